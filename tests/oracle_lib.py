@@ -1,0 +1,233 @@
+"""ctypes access to the parity checkers (TEST INFRASTRUCTURE).
+
+`Oracle("port")`  -> oracle/libmonty_oracle.so   (plain-C restatement)
+`Oracle("reference")` -> oracle/_ref/libmonty_ref.so (unmodified reference headers)
+
+Both expose the same operations with the same semantics as the reference's
+cpp11 layer (src/random.cpp, src/density.cpp); states are numpy uint64 arrays
+of shape (n_streams, 4) updated in place.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+GEN_NAMES = [
+    "xoshiro256plus", "xoshiro256plusplus", "xoshiro256starstar",
+    "xoshiro128plus", "xoshiro128plusplus", "xoshiro128starstar",
+    "xoroshiro128plus", "xoroshiro128plusplus", "xoroshiro128starstar",
+    "xoshiro512plus", "xoshiro512plusplus", "xoshiro512starstar",
+]
+
+DIST = {
+    "real": 0, "uniform": 1, "exponential_rate": 2, "exponential_mean": 3,
+    "normal_box_muller": 4, "normal_polar": 5, "normal_ziggurat": 6,
+    "binomial": 7, "poisson": 8, "gamma_scale": 9, "gamma_rate": 10,
+    "beta": 11, "negative_binomial_prob": 12, "negative_binomial_mu": 13,
+    "hypergeometric": 14, "truncated_normal": 15, "cauchy": 16, "weibull": 17,
+    "log_normal": 18, "beta_binomial_prob": 19, "beta_binomial_ab": 20,
+    "zi_poisson": 21, "zi_negative_binomial_prob": 22,
+    "zi_negative_binomial_mu": 23,
+}
+N_PARAMS = [0, 2, 1, 1, 2, 2, 2, 2, 1, 2, 2, 2, 2, 2, 3, 4, 2, 2, 2, 3, 3, 2, 3, 3]
+
+DENS = {
+    "binomial": 0, "normal": 1, "negative_binomial_mu": 2,
+    "negative_binomial_prob": 3, "beta_binomial_prob": 4,
+    "beta_binomial_ab": 5, "poisson": 6, "uniform": 7, "exponential_rate": 8,
+    "exponential_mean": 9, "gamma_rate": 10, "gamma_scale": 11, "beta": 12,
+    "hypergeometric": 13, "log_normal": 14, "truncated_normal": 15,
+    "cauchy": 16, "weibull": 17, "zi_poisson": 18,
+    "zi_negative_binomial_mu": 19, "zi_negative_binomial_prob": 20,
+}
+
+
+def build_oracles():
+    """(Re)build the checkers; `make ref` is a no-op without /root/reference."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "all"], check=True)
+
+
+def have_reference():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libmonty_ref.so"))
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+class Oracle:
+    def __init__(self, kind="port"):
+        self.kind = kind
+        if kind == "port":
+            path = os.path.join(ORACLE_DIR, "libmonty_oracle.so")
+            self.px = "orc_"
+        elif kind == "reference":
+            path = os.path.join(ORACLE_DIR, "_ref", "libmonty_ref.so")
+            self.px = "ref_"
+        else:
+            raise ValueError(kind)
+        if not os.path.exists(path):
+            build_oracles()
+        self.lib = C.CDLL(path)
+        self._fn("last_error").restype = C.c_char_p
+        self._fn("max_threads").restype = C.c_int
+
+    def _fn(self, name):
+        return getattr(self.lib, self.px + name)
+
+    def _err(self):
+        return self._fn("last_error")().decode()
+
+    def max_threads(self):
+        return int(self._fn("max_threads")())
+
+    # -- generator ---------------------------------------------------------
+    def seed_states(self, seed, n_streams, raw_words=None):
+        out = np.zeros((n_streams, 4), dtype=np.uint64)
+        if self.kind == "port":
+            if raw_words is None:
+                words, nw = None, 0
+            else:
+                raw_words = np.ascontiguousarray(raw_words, dtype=np.uint64).ravel()
+                words, nw = raw_words.ctypes.data_as(C.c_void_p), raw_words.size
+            rc = self.lib.orc_seed_states(C.c_uint64(seed), words, C.c_size_t(nw),
+                                          C.c_size_t(n_streams),
+                                          out.ctypes.data_as(C.c_void_p))
+        elif raw_words is None:
+            rc = self.lib.ref_seed_states(C.c_uint64(seed), C.c_size_t(n_streams),
+                                          out.ctypes.data_as(C.c_void_p))
+        else:
+            raw_words = np.ascontiguousarray(raw_words, dtype=np.uint64).ravel()
+            rc = self.lib.ref_seed_states_raw(raw_words.ctypes.data_as(C.c_void_p),
+                                              C.c_size_t(raw_words.size),
+                                              C.c_size_t(n_streams),
+                                              out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise OracleError(self._err())
+        return out
+
+    def jump(self, state, n=1, long=False):
+        assert state.dtype == np.uint64 and state.flags.c_contiguous
+        self._fn("jump")(state.ctypes.data_as(C.c_void_p), C.c_size_t(state.shape[0]),
+                         C.c_int(n), C.c_int(1 if long else 0))
+        return state
+
+    def raw(self, gen, state, n_samples):
+        out = np.zeros((state.shape[0], n_samples), dtype=np.uint64)
+        rc = self._fn("raw")(C.c_int(gen), state.ctypes.data_as(C.c_void_p),
+                             C.c_size_t(state.shape[0]), C.c_size_t(n_samples),
+                             out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise OracleError(self._err())
+        return out
+
+    def xoshiro_run(self, gen, seed=42, n=10):
+        vals = np.zeros(3 * n, dtype=np.uint64)
+        st = np.zeros(8, dtype=np.uint64)
+        nw = C.c_int(0)
+        rc = self._fn("xoshiro_run")(C.c_int(gen), C.c_uint64(seed), C.c_int(n),
+                                     vals.ctypes.data_as(C.c_void_p),
+                                     st.ctypes.data_as(C.c_void_p), C.byref(nw))
+        if rc != 0:
+            raise OracleError(self._err())
+        return vals, st[:nw.value]
+
+    # -- samplers ----------------------------------------------------------
+    def sample(self, dist, state, n_samples, params=(), real_type="f64",
+               deterministic=False, n_threads=1):
+        """Returns array (n_streams, n_samples); `state` advanced in place.
+        On a parameter error raises OracleError (state stays partially
+        advanced, as in the reference)."""
+        d = DIST[dist] if isinstance(dist, str) else dist
+        n_streams = state.shape[0]
+        arrs = [np.ascontiguousarray(np.atleast_1d(p), dtype=np.float64) for p in params]
+        assert len(arrs) == N_PARAMS[d], (dist, len(arrs))
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs] + [None] * (4 - len(arrs)))
+        lens = (C.c_size_t * 4)(*[a.size for a in arrs] + [0] * (4 - len(arrs)))
+        out = np.full((n_streams, n_samples), np.nan, dtype=np.float64)
+        rc = self._fn("sample")(C.c_int(d), C.c_int(1 if real_type == "f32" else 0),
+                                state.ctypes.data_as(C.c_void_p), C.c_size_t(n_streams),
+                                C.c_int(1 if deterministic else 0),
+                                C.c_size_t(n_samples), ptrs, lens,
+                                out.ctypes.data_as(C.c_void_p), C.c_int(n_threads))
+        if rc != 0:
+            raise OracleError(self._err())
+        return out
+
+    def multinomial(self, state, n_samples, size, prob, deterministic=False):
+        n_streams = state.shape[0]
+        size = np.ascontiguousarray(np.atleast_1d(size), dtype=np.float64)
+        prob = np.asarray(prob, dtype=np.float64)
+        if prob.ndim == 1:
+            prob_len, prob_cols = prob.size, 1
+            pf = np.ascontiguousarray(prob)
+        else:  # (prob_len, cols) R matrix -> column-major memory
+            prob_len, prob_cols = prob.shape
+            pf = np.ascontiguousarray(prob.T)
+        out = np.zeros((n_streams, n_samples, prob_len), dtype=np.float64)
+        if self.kind == "port":
+            rc = self.lib.orc_multinomial(state.ctypes.data_as(C.c_void_p),
+                                          C.c_size_t(n_streams),
+                                          C.c_int(1 if deterministic else 0),
+                                          C.c_size_t(n_samples),
+                                          size.ctypes.data_as(C.c_void_p), C.c_size_t(size.size),
+                                          pf.ctypes.data_as(C.c_void_p), C.c_size_t(prob_len),
+                                          C.c_size_t(prob_cols),
+                                          out.ctypes.data_as(C.c_void_p))
+        else:
+            assert not deterministic
+            rc = self.lib.ref_multinomial(state.ctypes.data_as(C.c_void_p),
+                                          C.c_size_t(n_streams), C.c_size_t(n_samples),
+                                          size.ctypes.data_as(C.c_void_p), C.c_size_t(size.size),
+                                          pf.ctypes.data_as(C.c_void_p), C.c_size_t(prob_len),
+                                          C.c_size_t(prob_cols),
+                                          out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise OracleError(self._err())
+        return out
+
+    # -- densities ---------------------------------------------------------
+    def density(self, dens, x, params, log=True, real_type="f64", n_threads=1):
+        d = DENS[dens] if isinstance(dens, str) else dens
+        keep = []
+
+        def prep(a):
+            a = np.asarray(a)
+            if a.dtype.kind in "iu":
+                a = np.ascontiguousarray(a, dtype=np.int32)
+                keep.append(a)
+                return a.ctypes.data, 1
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return a.ctypes.data, 0
+
+        xp, xi = prep(x)
+        n = keep[0].size
+        pp = [prep(p) for p in params]
+        ptrs = (C.c_void_p * 4)(*[p[0] for p in pp] + [None] * (4 - len(pp)))
+        isi = (C.c_int * 4)(*[p[1] for p in pp] + [0] * (4 - len(pp)))
+        out = np.zeros(n, dtype=np.float64)
+        rc = self._fn("density")(C.c_int(d), C.c_int(1 if real_type == "f32" else 0),
+                                 C.c_size_t(n), C.c_void_p(xp), C.c_int(xi), ptrs, isi,
+                                 C.c_int(1 if log else 0),
+                                 out.ctypes.data_as(C.c_void_p), C.c_int(n_threads))
+        if rc != 0:
+            raise OracleError(self._err())
+        return out
+
+
+def counter_hash(i, k):
+    """The seed-defined parameter hash of SURVEY 8(d): h(i, k) in (0, 1).
+    h = int_to_real<double>(splitmix64(0x9E3779B97F4A7C15*(2*(i*8+k)+1) ^ 0xC0FFEE))."""
+    i = np.asarray(i, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (np.uint64(0x9E3779B97F4A7C15) * (np.uint64(2) * (i * np.uint64(8) + np.uint64(k)) + np.uint64(1))) ^ np.uint64(0xC0FFEE)
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * 1.1102230246251565e-16 + 1.1102230246251565e-16 / 2.0
