@@ -1,0 +1,17 @@
+// sample_dispatch.h -- host-callable launchers, one per group of samplers.
+// The groups only exist to compile the kernel instantiations in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include "launch_args.h"
+
+namespace mb200 {
+// Each returns cudaErrorInvalidValue if `dist` is not in its group.
+cudaError_t launch_sample_group_a(int dist, int real_type, int out_f32, bool validate_only,
+                                  const SampleArgs& a, int sm_count, cudaStream_t st);
+cudaError_t launch_sample_group_b(int dist, int real_type, int out_f32, bool validate_only,
+                                  const SampleArgs& a, int sm_count, cudaStream_t st);
+cudaError_t launch_sample_group_c(int dist, int real_type, int out_f32, bool validate_only,
+                                  const SampleArgs& a, int sm_count, cudaStream_t st);
+bool dist_in_group_a(int dist);
+bool dist_in_group_b(int dist);
+}  // namespace mb200

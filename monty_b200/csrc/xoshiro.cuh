@@ -1,0 +1,119 @@
+// xoshiro.cuh -- device-side generator: xoshiro256 {+,++,**} state held in
+// registers, next(), int->real conversion, and the generic polynomial jump.
+//
+// ref: inst/include/monty/random/xoshiro256.hpp:65-103 (next),
+//      utils.hpp:14-44 (int_to_real), generator.hpp:86-106 (rng_jump_state).
+// "hdr/" below abbreviates inst/include/monty/random/ of the reference.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mb200 {
+
+enum Scrambler { kPlus = 0, kPlusPlus = 1, kStarStar = 2 };
+
+// One stream's generator state, 4 x u64, exactly the reference's exported
+// layout (hdr/prng.hpp:92-105).  Lives in registers while a kernel runs.
+struct X256 {
+  uint64_t s0, s1, s2, s3;
+};
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) {
+  return (x << k) | (x >> (64 - k));
+}
+
+// 128-bit vectorised state load / store: a stream's state is 32 contiguous,
+// 32-byte aligned bytes (cudaMalloc'd base, 32 B stride).
+__device__ __forceinline__ X256 load_state(const uint64_t* __restrict__ state, size_t stream) {
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(state + 4 * stream);
+  const ulonglong2 a = p[0];
+  const ulonglong2 b = p[1];
+  return X256{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void store_state(uint64_t* __restrict__ state, size_t stream, const X256& s) {
+  ulonglong2* p = reinterpret_cast<ulonglong2*>(state + 4 * stream);
+  p[0] = make_ulonglong2(s.s0, s.s1);
+  p[1] = make_ulonglong2(s.s2, s.s3);
+}
+
+// The linear state transition shared by the three scramblers
+// (hdr/xoshiro256.hpp:68-75).  Written with the two 3-input xors the update
+// collapses to, so each 32-bit half is a single LOP3:
+//   s1' = s1 ^ s2 ^ s0,  s0' = s0 ^ s3 ^ s1,  s2' = s2 ^ s0 ^ (s1 << 17),
+//   s3' = rotl(s3 ^ s1, 45)
+__device__ __forceinline__ void x256_step(X256& s) {
+  const uint64_t t = s.s1 << 17;
+  const uint64_t n2 = s.s2 ^ s.s0;
+  const uint64_t n3 = s.s3 ^ s.s1;
+  s.s1 ^= n2;
+  s.s0 ^= n3;
+  s.s2 = n2 ^ t;
+  s.s3 = rotl64(n3, 45);
+}
+
+template <int SCR>
+__device__ __forceinline__ uint64_t x256_next(X256& s) {
+  uint64_t result;
+  if (SCR == kPlus) {
+    result = s.s0 + s.s3;                      // hdr/xoshiro256.hpp:93
+  } else if (SCR == kPlusPlus) {
+    result = rotl64(s.s0 + s.s3, 23) + s.s0;   // hdr/xoshiro256.hpp:80
+  } else {
+    result = rotl64(s.s1 * 5, 7) * 9;          // hdr/xoshiro256.hpp:67
+  }
+  x256_step(s);
+  return result;
+}
+
+// The sampler generator is xoshiro256+ (the reference's default_rng64,
+// src/random.cpp:10).
+struct Rng {
+  X256 s;
+  __device__ __forceinline__ uint64_t next() { return x256_next<kPlus>(s); }
+};
+
+// hdr/utils.hpp:21-25: (x >> 11) * 2^-53 + 2^-54.  The product is a scaling
+// by a power of two, hence exact, so one explicit FMA rounds exactly like the
+// reference's separate multiply and add.
+__device__ __forceinline__ double u64_to_double(uint64_t x) {
+  return __fma_rn(static_cast<double>(x >> 11), 1.1102230246251565e-16,
+                  (1.1102230246251565e-16 / 2.0));
+}
+// hdr/utils.hpp:33-38: the top 32 bits, converted to float (one rounding),
+// scaled by 2^-32 (exact; 2.3283064e-10f is 2^-32), plus 2^-33.
+__device__ __forceinline__ float u64_to_float(uint64_t x) {
+  const uint32_t t = static_cast<uint32_t>(x >> 32);
+  return __fmaf_rn(static_cast<float>(t), 2.3283064e-10f, (2.3283064e-10f / 2.0f));
+}
+
+template <typename T> __device__ __forceinline__ T int_to_real(uint64_t x);
+template <> __device__ __forceinline__ double int_to_real<double>(uint64_t x) { return u64_to_double(x); }
+template <> __device__ __forceinline__ float int_to_real<float>(uint64_t x) { return u64_to_float(x); }
+
+// hdr/generator.hpp:154-159
+template <typename T>
+__device__ __forceinline__ T random_real(Rng& r) {
+  return int_to_real<T>(r.next());
+}
+
+// hdr/generator.hpp:86-106: advance by the polynomial `coef` (256 bits, word 0
+// bit 0 first): acc ^= state when the bit is set, then step.  With coef = the
+// reference's jump / long_jump constants this IS jump() / long_jump(); with
+// coef = x^(k * 2^128) mod P it is k jumps at the cost of one (see
+// jump_poly.h).
+__device__ __forceinline__ void x256_apply_poly(X256& s, const uint64_t* __restrict__ coef) {
+  uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 1
+  for (int w = 0; w < 4; ++w) {
+    const uint64_t c = coef[w];
+#pragma unroll 4
+    for (int b = 0; b < 64; ++b) {
+      const uint64_t m = 0 - ((c >> b) & 1ull);   // all-ones when the bit is set
+      a0 ^= s.s0 & m; a1 ^= s.s1 & m; a2 ^= s.s2 & m; a3 ^= s.s3 & m;
+      x256_step(s);
+    }
+  }
+  s.s0 = a0; s.s1 = a1; s.s2 = a2; s.s3 = a3;
+}
+
+}  // namespace mb200
