@@ -6,7 +6,7 @@ call the C-ABI of include/monty_b200.h through ctypes, in the same way the
 reference's R functions call its cpp11 layer.  All arithmetic happens in CUDA
 kernels (monty_b200/csrc); nothing falls back to the CPU.
 """
-from ._lib import MontyError, lib as _lib  # noqa: F401
+from ._lib import MontyError  # noqa: F401
 from .random import *  # noqa: F401,F403
 from .random import __all__ as _random_all
 from . import density  # noqa: F401

@@ -207,7 +207,7 @@ int mb200_rng_create(uint64_t seed, const uint8_t* seed_state_host, size_t seed_
   } else {
     seeds.resize(4);
     uint64_t s = seed;
-    for (int i = 0; i < 4; ++i) seeds[i] = host_splitmix64(s);
+    for (int i = 0; i < 4; ++i) seeds[i] = s = host_splitmix64(s);   // generator.hpp:118-121
   }
   const size_t n_seed = seeds.size() / 4;
   if (long_jumps > 0) {

@@ -36,7 +36,7 @@ inline void host_x256_step(uint64_t s[4]) {   // hdr/xoshiro256.hpp:68-75
   s[3] = (s[3] << 45) | (s[3] >> 19);
 }
 
-inline uint64_t host_splitmix64(uint64_t& seed) {   // hdr/utils.hpp:72-77
+inline uint64_t host_splitmix64(uint64_t seed) {   // hdr/utils.hpp:72-77
   uint64_t z = (seed += 0x9e3779b97f4a7c15ull);
   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
   z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;

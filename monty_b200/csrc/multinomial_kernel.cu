@@ -19,7 +19,7 @@ multinomial_kernel(uint64_t* __restrict__ state, unsigned long long n_streams,
   __shared__ TableSmem ts;
   Ctx ctx;
   ctx.err = 0;
-  stage_tables<void, kTailTables>(&ts, ctx);
+  stage_tables<kTailTables>(&ts, ctx);
   const unsigned long long stream = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (stream >= n_streams) return;
   const double* pr = prob + static_cast<unsigned long long>(prob_stride) * stream * prob_len;

@@ -1,7 +1,8 @@
 // sample_kernel.cuh -- the sampling kernels: one thread per stream, generator
 // state in registers for the whole batch of draws, per-warp shared-memory
 // staging so that the stream-major output y[n_samples * stream + sample]
-// (ref: src/random.cpp:220-224) is written with fully coalesced stores.
+// (ref: src/random.cpp:220-224) is written with fully coalesced, line-aligned
+// 128-bit stores.
 //
 // Layout in HBM
 //   state  uint64[n_streams][4]    32 B per stream, 2 x 128-bit load/store
@@ -9,15 +10,29 @@
 //   out    OutT[n_streams][n_samples]  (stream-major == R's column-major
 //          [n_samples x n_streams])
 //
-// Work decomposition.  A warp owns 32 consecutive streams.  Lane l draws for
-// stream 32w + l and parks its draws in row l of the warp's shared-memory
-// tile [32][TILE+1]; after TILE draws the warp turns the tile round: in step
-// r all 32 lanes write the TILE consecutive values of stream 32w + r, i.e.
-// one contiguous TILE * sizeof(OutT) run per store instruction.  The +1
-// padding makes both the column writes and the row reads bank-conflict free.
-// Warps never synchronise with each other; the grid is sized as a multiple of
-// the SM count and strides over warp-tiles.
+// Work decomposition.  A warp owns 32 consecutive streams; lane l draws for
+// stream 32w + l.  Think of `out` as one long array indexed by the global
+// element g = stream * n_samples + sample.  Row r's draws occupy
+// [B_r, B_r + n_samples), B_r = (32w + r) * n_samples.  The warp walks each
+// row in WINDOWS of kTile elements aligned in g (window k of row r covers
+// [A_r + kTile*k, A_r + kTile*(k+1)), A_r = B_r rounded down to kTile), so a
+// window is a whole number of 128-byte lines whatever n_samples is.  (With
+// windows aligned in `sample` instead, n_samples = 1000 put every other row
+// 64 B off the line grid, and the half-written lines left L2 before their
+// other half arrived: 4.6 TB/s instead of 6.0 TB/s on a pure-store
+// microbenchmark, profiles/r01_write_pattern.txt.)
+//
+// Per window: lane l computes the draws of ITS row that fall into the window
+// and parks them in row l of the warp's shared-memory tile [32][PITCH]; then
+// the warp turns the tile round: each store instruction writes whole rows
+// (2 rows x 256 B for double) with 16 bytes per lane.  The row pitch is an odd
+// number of 16-byte units, so both the column-wise STS.128 and the row-wise
+// LDS.128 are bank-conflict free.  First / last windows of a row are ragged
+// and take a masked scalar path.  Warps never synchronise with each other;
+// the grid is a multiple of the SM count and strides over warp-tiles.
 #pragma once
+#include <type_traits>
+
 #include "samplers.cuh"
 #include "launch_args.h"
 
@@ -33,8 +48,11 @@ static __device__ const float g_tail_f[128] = { MONTY_TAIL_F_VALUES };
 
 constexpr int kBlock = 128;           // 4 warps
 constexpr int kWarps = kBlock / 32;
-constexpr int kTile = 32;             // draws staged per lane before a write-out
-constexpr int kPitch = kTile + 1;
+constexpr int kTile = 32;             // window width in elements
+
+template <typename OutT> struct TileCfg;
+template <> struct TileCfg<double> { static constexpr int VEC = 2, PITCH = 34; };
+template <> struct TileCfg<float> { static constexpr int VEC = 4, PITCH = 36; };
 
 struct __align__(16) TableSmem {
   double2 zig_xy[256];
@@ -58,7 +76,7 @@ template <typename OutT> __device__ __forceinline__ OutT out_nan();
 template <> __device__ __forceinline__ double out_nan<double>() { return __longlong_as_double(0x7ff8000000000000ll); }
 template <> __device__ __forceinline__ float out_nan<float>() { return __int_as_float(0x7fc00000); }
 
-template <class D, int TABLES>
+template <int TABLES>
 __device__ __forceinline__ void stage_tables(TableSmem* ts, Ctx& ctx) {
   if (TABLES == kZigTables) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) ts->zig_xy[i] = g_zig_xy[i];
@@ -75,33 +93,101 @@ __device__ __forceinline__ void stage_tables(TableSmem* ts, Ctx& ctx) {
   if (TABLES != kNoTables) __syncthreads();
 }
 
+__device__ __forceinline__ void st_vec(double* p, const double* v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+__device__ __forceinline__ void st_vec(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// One warp's description of its 32 rows.
+struct WarpRows {
+  unsigned long long s_first;     // first stream of the warp
+  unsigned long long n_samples;
+  int n_rows;                     // rows that exist (n_streams may end inside the warp)
+};
+
+// g-aligned start of row r's window 0
+__device__ __forceinline__ unsigned long long row_window_base(const WarpRows& w, int r) {
+  return ((w.s_first + r) * w.n_samples) & ~static_cast<unsigned long long>(kTile - 1);
+}
+
+// Vector write-out of a window in which every element of every row is valid.
+// All loads first, then all stores: the LDS latency is paid once per window
+// and no register is rewritten while a store still owns it.
+template <typename OutT>
+__device__ __forceinline__ void write_window_full(const OutT* tile, OutT* out, const WarpRows& w,
+                                                  unsigned long long k, int lane) {
+  constexpr int VEC = TileCfg<OutT>::VEC;
+  constexpr int PITCH = TileCfg<OutT>::PITCH;
+  constexpr int LPR = kTile / VEC;         // lanes per row: 16 (double), 8 (float)
+  constexpr int RPI = 32 / LPR;            // rows per instruction: 2 or 4
+  constexpr int STEPS = 32 / RPI;          // 16 or 8
+  using V = typename std::conditional<sizeof(OutT) == 8, double2, float4>::type;
+  const int sub = (lane % LPR) * VEC;
+  const int rsub = lane / LPR;
+  V v[STEPS];
+#pragma unroll
+  for (int t = 0; t < STEPS; ++t) {
+    v[t] = *reinterpret_cast<const V*>(tile + (rsub + t * RPI) * PITCH + sub);
+  }
+#pragma unroll
+  for (int t = 0; t < STEPS; ++t) {
+    const int r = rsub + t * RPI;
+    OutT* dst = out + row_window_base(w, r) + k * kTile + sub;
+    *reinterpret_cast<V*>(dst) = v[t];
+  }
+}
+
+// Masked write-out for ragged windows (first / last of a row, short rows,
+// missing rows): lane e of step r writes element e of row r if it belongs to
+// the row.
+template <typename OutT>
+__device__ __forceinline__ void write_window_edge(const OutT* tile, OutT* out, const WarpRows& w,
+                                                  unsigned long long k, int lane) {
+  constexpr int PITCH = TileCfg<OutT>::PITCH;
+  for (int r = 0; r < w.n_rows; ++r) {
+    const unsigned long long b = (w.s_first + r) * w.n_samples;
+    const unsigned long long g = row_window_base(w, r) + k * kTile + lane;
+    if (g >= b && g < b + w.n_samples) out[g] = tile[r * PITCH + lane];
+  }
+}
+
 // T: real_type of the computation; OutT: element type of `out`.
 template <class D, typename T, typename OutT>
 __global__ void __launch_bounds__(kBlock)
 sample_kernel(const SampleArgs a) {
+  constexpr int VEC = TileCfg<OutT>::VEC;
+  constexpr int PITCH = TileCfg<OutT>::PITCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   OutT* tile_all = reinterpret_cast<OutT*>(smem_raw);
-  TableSmem* ts = reinterpret_cast<TableSmem*>(smem_raw + sizeof(OutT) * kWarps * 32 * kPitch);
+  TableSmem* ts = reinterpret_cast<TableSmem*>(smem_raw + sizeof(OutT) * kWarps * 32 * PITCH);
 
   Ctx ctx;
   ctx.err = 0;
-  stage_tables<D, D::TABLES>(ts, ctx);
+  stage_tables<D::TABLES>(ts, ctx);
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  OutT* tile = tile_all + warp * 32 * kPitch;
+  OutT* tile = tile_all + warp * 32 * PITCH;
   OutT* out = static_cast<OutT*>(a.out);
 
   const unsigned long long n_streams = a.n_streams;
   const unsigned long long n_samples = a.n_samples;
   const unsigned long long n_warp_tiles = (n_streams + 31) / 32;
   const unsigned long long warp_stride = static_cast<unsigned long long>(gridDim.x) * kWarps;
+  // 128-bit stores need every row to start on a 16-byte boundary
+  const bool vec_ok = (n_samples % VEC == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
   for (unsigned long long wt = static_cast<unsigned long long>(blockIdx.x) * kWarps + warp;
        wt < n_warp_tiles; wt += warp_stride) {
-    const unsigned long long s_first = wt * 32;
-    const unsigned long long stream = s_first + lane;
-    bool live = stream < n_streams;
+    WarpRows w;
+    w.s_first = wt * 32;
+    w.n_samples = n_samples;
+    w.n_rows = (n_streams - w.s_first) < 32 ? static_cast<int>(n_streams - w.s_first) : 32;
+    const unsigned long long stream = w.s_first + lane;
+    const bool exists = stream < n_streams;
+    bool live = exists;
 
     Rng rng;
     typename D::Prep prep;
@@ -123,7 +209,7 @@ sample_kernel(const SampleArgs a) {
     if (n_samples == 1) {
       // one draw per stream (monty_random_<dist>, the SIR-step shape):
       // consecutive lanes write consecutive elements, no staging needed
-      if (stream < n_streams) {
+      if (exists) {
         OutT y = out_nan<OutT>();
         if (live) {
           y = static_cast<OutT>(D::draw(rng, prep, ctx));
@@ -136,34 +222,57 @@ sample_kernel(const SampleArgs a) {
         out[stream] = y;
       }
     } else {
-      const int n_rows = (n_streams - s_first) < 32 ? static_cast<int>(n_streams - s_first) : 32;
-      for (unsigned long long j0 = 0; j0 < n_samples; j0 += kTile) {
-        const int len = (n_samples - j0) < kTile ? static_cast<int>(n_samples - j0) : kTile;
-        OutT* row = tile + lane * kPitch;
+      OutT* row = tile + lane * PITCH;
+      // this lane's row: sample j sits in slot (m + j) % kTile of window
+      // (m + j) / kTile, m = offset of the row start inside its window 0
+      const int m = static_cast<int>((stream * n_samples) & (kTile - 1));
+      // the warp walks as many windows as a row can span
+      const unsigned long long n_windows = (n_samples + 2 * (kTile - 1)) / kTile;
+      for (unsigned long long k = 0; k < n_windows; ++k) {
+        // slots [e_lo, e_hi) of window k belong to this lane's row
+        const long long j_first = static_cast<long long>(k * kTile) - m;   // sample index of slot 0
+        const int e_lo = j_first < 0 ? static_cast<int>(-j_first) : 0;
+        const long long rem = static_cast<long long>(n_samples) - j_first;
+        const int e_hi = !exists ? 0 : (rem >= kTile ? kTile : (rem > 0 ? static_cast<int>(rem) : 0));
+        if (!__any_sync(0xffffffffu, e_hi > e_lo)) continue;   // nobody has data in this window
+        const bool row_full = e_lo == 0 && e_hi == kTile;
+        const bool all_full = vec_ok && __all_sync(0xffffffffu, row_full);
         if (live) {
-          for (int j = 0; j < len; ++j) {
-            row[j] = static_cast<OutT>(D::draw(rng, prep, ctx));
-            if (D::DYN_ERR && ctx.err) {
-              report_error(a.err, stream, ctx.err, ctx.err_vals);
-              ctx.err = 0;
-              live = false;
-              for (int jj = j; jj < len; ++jj) row[jj] = out_nan<OutT>();
-              break;
+          if (all_full && D::UNROLL == 2) {
+            // tiny draw(): the whole window straight-line, VEC draws per store
+#pragma unroll
+            for (int j = 0; j < kTile; j += VEC) {
+              OutT v[VEC];
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) v[e] = static_cast<OutT>(D::draw(rng, prep, ctx));
+              st_vec(row + j, v);
             }
+          } else if (all_full && D::UNROLL == 1) {
+#pragma unroll 1
+            for (int j = 0; j < kTile; j += VEC) {
+              OutT v[VEC];
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) v[e] = static_cast<OutT>(D::draw(rng, prep, ctx));
+              st_vec(row + j, v);
+            }
+          } else {
+#pragma unroll 1
+            for (int e = e_lo; e < e_hi; ++e) row[e] = static_cast<OutT>(D::draw(rng, prep, ctx));
           }
-        } else {
-          for (int j = 0; j < len; ++j) row[j] = out_nan<OutT>();
+          if (D::DYN_ERR && ctx.err) {
+            // a data-dependent failure inside a composition: the stream is
+            // abandoned and the rest of its output is NaN
+            report_error(a.err, stream, ctx.err, ctx.err_vals);
+            ctx.err = 0;
+            live = false;
+          }
+        }
+        if (!live) {
+          for (int e = e_lo; e < e_hi; ++e) row[e] = out_nan<OutT>();
         }
         __syncwarp();
-        // write-out: step r stores stream (s_first + r)'s `len` consecutive draws
-        OutT* dst = out + s_first * n_samples + j0 + lane;
-        const OutT* src = tile + lane;
-        if (lane < len) {
-#pragma unroll 4
-          for (int r = 0; r < n_rows; ++r) {
-            dst[r * n_samples] = src[r * kPitch];
-          }
-        }
+        if (all_full) write_window_full<OutT>(tile, out, w, k, lane);
+        else write_window_edge<OutT>(tile, out, w, k, lane);
         __syncwarp();
       }
     }
@@ -196,7 +305,7 @@ validate_kernel(const SampleArgs a) {
 
 template <typename OutT>
 inline size_t sample_smem_bytes(int tables) {
-  size_t b = sizeof(OutT) * kWarps * 32 * kPitch;
+  size_t b = sizeof(OutT) * kWarps * 32 * TileCfg<OutT>::PITCH;
   b = (b + 15) & ~static_cast<size_t>(15);
   if (tables != kNoTables) b += sizeof(TableSmem);
   return b;

@@ -37,18 +37,32 @@ __device__ __forceinline__ void store_state(uint64_t* __restrict__ state, size_t
 }
 
 // The linear state transition shared by the three scramblers
-// (hdr/xoshiro256.hpp:68-75).  Written with the two 3-input xors the update
-// collapses to, so each 32-bit half is a single LOP3:
+// (hdr/xoshiro256.hpp:68-75), on explicit 32-bit halves so that it costs the
+// minimum the ALU pipe allows -- 8 three-input LOP3, 3 funnel shifts and one
+// shift (which the compiler issues as IMAD.SHL on the FMA pipe):
 //   s1' = s1 ^ s2 ^ s0,  s0' = s0 ^ s3 ^ s1,  s2' = s2 ^ s0 ^ (s1 << 17),
-//   s3' = rotl(s3 ^ s1, 45)
+//   s3' = rotl(s3 ^ s1, 45) = swap halves, then rotate left by 13
+// The 64-bit formulation made ptxas spend 5 more ALU ops per step on the
+// rotate and on two-input xors; the uniform kernel is ALU-pipe bound, so this
+// is worth 25% of its throughput (profiles/r01_*).
 __device__ __forceinline__ void x256_step(X256& s) {
-  const uint64_t t = s.s1 << 17;
-  const uint64_t n2 = s.s2 ^ s.s0;
-  const uint64_t n3 = s.s3 ^ s.s1;
-  s.s1 ^= n2;
-  s.s0 ^= n3;
-  s.s2 = n2 ^ t;
-  s.s3 = rotl64(n3, 45);
+  const uint32_t s0l = static_cast<uint32_t>(s.s0), s0h = static_cast<uint32_t>(s.s0 >> 32);
+  const uint32_t s1l = static_cast<uint32_t>(s.s1), s1h = static_cast<uint32_t>(s.s1 >> 32);
+  const uint32_t s2l = static_cast<uint32_t>(s.s2), s2h = static_cast<uint32_t>(s.s2 >> 32);
+  const uint32_t s3l = static_cast<uint32_t>(s.s3), s3h = static_cast<uint32_t>(s.s3 >> 32);
+  const uint32_t tl = s1l << 17;
+  const uint32_t th = __funnelshift_l(s1l, s1h, 17);
+  const uint32_t n3l = s3l ^ s1l, n3h = s3h ^ s1h;
+  const uint32_t r1l = s1l ^ s2l ^ s0l, r1h = s1h ^ s2h ^ s0h;
+  const uint32_t r0l = s0l ^ n3l, r0h = s0h ^ n3h;
+  const uint32_t r2l = s2l ^ s0l ^ tl, r2h = s2h ^ s0h ^ th;
+  // rotl64(n3, 45): (hi, lo) -> hi' = (lo << 13) | (hi >> 19), lo' = (hi << 13) | (lo >> 19)
+  const uint32_t r3h = __funnelshift_l(n3h, n3l, 13);
+  const uint32_t r3l = __funnelshift_l(n3l, n3h, 13);
+  s.s0 = (static_cast<uint64_t>(r0h) << 32) | r0l;
+  s.s1 = (static_cast<uint64_t>(r1h) << 32) | r1l;
+  s.s2 = (static_cast<uint64_t>(r2h) << 32) | r2l;
+  s.s3 = (static_cast<uint64_t>(r3h) << 32) | r3l;
 }
 
 template <int SCR>
@@ -72,11 +86,13 @@ struct Rng {
   __device__ __forceinline__ uint64_t next() { return x256_next<kPlus>(s); }
 };
 
-// hdr/utils.hpp:21-25: (x >> 11) * 2^-53 + 2^-54.  The product is a scaling
-// by a power of two, hence exact, so one explicit FMA rounds exactly like the
-// reference's separate multiply and add.
+// hdr/utils.hpp:21-25: (x >> 11) * 2^-53 + 2^-54.  Clearing the low 11 bits
+// leaves at most 53 significant bits, so the u64 -> f64 conversion is exact
+// and equals (x >> 11) * 2^11; scaling by 2^-64 is exact too, hence one
+// explicit FMA rounds exactly like the reference's multiply followed by add.
+// (One LOP3 on the low word instead of a two-instruction 64-bit shift.)
 __device__ __forceinline__ double u64_to_double(uint64_t x) {
-  return __fma_rn(static_cast<double>(x >> 11), 1.1102230246251565e-16,
+  return __fma_rn(__ull2double_rn(x & ~0x7ffull), 5.421010862427522170e-20 /* 2^-64 */,
                   (1.1102230246251565e-16 / 2.0));
 }
 // hdr/utils.hpp:33-38: the top 32 bits, converted to float (one rounding),
