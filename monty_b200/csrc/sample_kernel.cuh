@@ -82,6 +82,7 @@ __device__ __forceinline__ void stage_tables(TableSmem* ts, Ctx& ctx) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) ts->zig_xy[i] = g_zig_xy[i];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) ts->zig_x[i] = g_zig_x[i];
     ctx.zig_xy = ts->zig_xy;
+    ctx.zig_xy_saddr = smem_addr(ts->zig_xy);
     ctx.zig_x = ts->zig_x;
   }
   if (TABLES == kTailTables) {
@@ -93,12 +94,8 @@ __device__ __forceinline__ void stage_tables(TableSmem* ts, Ctx& ctx) {
   if (TABLES != kNoTables) __syncthreads();
 }
 
-__device__ __forceinline__ void st_vec(double* p, const double* v) {
-  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-}
-__device__ __forceinline__ void st_vec(float* p, const float* v) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
+__device__ __forceinline__ double2 lds_vec(uint32_t addr, double) { return lds_f64x2(addr); }
+__device__ __forceinline__ float4 lds_vec(uint32_t addr, float) { return lds_f32x4(addr); }
 
 // One warp's description of its 32 rows.
 struct WarpRows {
@@ -116,7 +113,7 @@ __device__ __forceinline__ unsigned long long row_window_base(const WarpRows& w,
 // All loads first, then all stores: the LDS latency is paid once per window
 // and no register is rewritten while a store still owns it.
 template <typename OutT>
-__device__ __forceinline__ void write_window_full(const OutT* tile, OutT* out, const WarpRows& w,
+__device__ __forceinline__ void write_window_full(uint32_t tile_saddr, OutT* out, const WarpRows& w,
                                                   unsigned long long k, int lane) {
   constexpr int VEC = TileCfg<OutT>::VEC;
   constexpr int PITCH = TileCfg<OutT>::PITCH;
@@ -126,16 +123,22 @@ __device__ __forceinline__ void write_window_full(const OutT* tile, OutT* out, c
   using V = typename std::conditional<sizeof(OutT) == 8, double2, float4>::type;
   const int sub = (lane % LPR) * VEC;
   const int rsub = lane / LPR;
-  V v[STEPS];
+  // two half-batches of 8 x 16 B: all loads of a batch first, then its stores
+  constexpr int HALF = STEPS / 2;
 #pragma unroll
-  for (int t = 0; t < STEPS; ++t) {
-    v[t] = *reinterpret_cast<const V*>(tile + (rsub + t * RPI) * PITCH + sub);
-  }
+  for (int h = 0; h < 2; ++h) {
+    V v[HALF];
 #pragma unroll
-  for (int t = 0; t < STEPS; ++t) {
-    const int r = rsub + t * RPI;
-    OutT* dst = out + row_window_base(w, r) + k * kTile + sub;
-    *reinterpret_cast<V*>(dst) = v[t];
+    for (int t = 0; t < HALF; ++t) {
+      const int r = rsub + (h * HALF + t) * RPI;
+      v[t] = lds_vec(tile_saddr + static_cast<uint32_t>((r * PITCH + sub) * sizeof(OutT)), OutT());
+    }
+#pragma unroll
+    for (int t = 0; t < HALF; ++t) {
+      const int r = rsub + (h * HALF + t) * RPI;
+      OutT* dst = out + row_window_base(w, r) + k * kTile + sub;
+      *reinterpret_cast<V*>(dst) = v[t];
+    }
   }
 }
 
@@ -155,7 +158,7 @@ __device__ __forceinline__ void write_window_edge(const OutT* tile, OutT* out, c
 
 // T: real_type of the computation; OutT: element type of `out`.
 template <class D, typename T, typename OutT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 5)
 sample_kernel(const SampleArgs a) {
   constexpr int VEC = TileCfg<OutT>::VEC;
   constexpr int PITCH = TileCfg<OutT>::PITCH;
@@ -223,6 +226,8 @@ sample_kernel(const SampleArgs a) {
       }
     } else {
       OutT* row = tile + lane * PITCH;
+      const uint32_t tile_saddr = smem_addr(tile);
+      const uint32_t row_saddr = tile_saddr + static_cast<uint32_t>(lane * PITCH * sizeof(OutT));
       // this lane's row: sample j sits in slot (m + j) % kTile of window
       // (m + j) / kTile, m = offset of the row start inside its window 0
       const int m = static_cast<int>((stream * n_samples) & (kTile - 1));
@@ -245,7 +250,7 @@ sample_kernel(const SampleArgs a) {
               OutT v[VEC];
 #pragma unroll
               for (int e = 0; e < VEC; ++e) v[e] = static_cast<OutT>(D::draw(rng, prep, ctx));
-              st_vec(row + j, v);
+              sts_vec(row_saddr + static_cast<uint32_t>(j * sizeof(OutT)), v);
             }
           } else if (all_full && D::UNROLL == 1) {
 #pragma unroll 1
@@ -253,7 +258,7 @@ sample_kernel(const SampleArgs a) {
               OutT v[VEC];
 #pragma unroll
               for (int e = 0; e < VEC; ++e) v[e] = static_cast<OutT>(D::draw(rng, prep, ctx));
-              st_vec(row + j, v);
+              sts_vec(row_saddr + static_cast<uint32_t>(j * sizeof(OutT)), v);
             }
           } else {
 #pragma unroll 1
@@ -271,7 +276,7 @@ sample_kernel(const SampleArgs a) {
           for (int e = e_lo; e < e_hi; ++e) row[e] = out_nan<OutT>();
         }
         __syncwarp();
-        if (all_full) write_window_full<OutT>(tile, out, w, k, lane);
+        if (all_full) write_window_full<OutT>(tile_saddr, out, w, k, lane);
         else write_window_edge<OutT>(tile, out, w, k, lane);
         __syncwarp();
       }
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(kBlock)
 validate_kernel(const SampleArgs a) {
   Ctx ctx;
   ctx.err = 0;
-  ctx.zig_xy = g_zig_xy; ctx.zig_x = g_zig_x; ctx.tail_d = g_tail_d; ctx.tail_f = g_tail_f;
+  ctx.zig_xy = g_zig_xy; ctx.zig_xy_saddr = 0; ctx.zig_x = g_zig_x; ctx.tail_d = g_tail_d; ctx.tail_f = g_tail_f;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long stream = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
        stream < a.n_streams; stream += stride) {
