@@ -14,7 +14,8 @@ def ulp_distance(a, b):
     ib = b.view(np.int64).astype(np.int64)
     ia = np.where(ia < 0, np.int64(-2 ** 63) - ia, ia)
     ib = np.where(ib < 0, np.int64(-2 ** 63) - ib, ib)
-    d = np.abs(ia.astype(np.float64) - ib.astype(np.float64))
+    with np.errstate(over="ignore"):
+        d = np.abs(ia - ib).astype(np.float64)      # exact: subtract as integers first
     d[(a == b) | (np.isnan(a) & np.isnan(b))] = 0
     return d
 
