@@ -210,6 +210,85 @@ def time_device(mb, torch, rng, dist, real, n_draws, params_dev, out, steps, war
     return total_ms, kernel_ms, wall
 
 
+def density_inputs(torch, name, n, first, dev):
+    """SURVEY 8(d) C5 inputs, generated on the device from the same counter hash."""
+    idx = torch.arange(first, first + n, dtype=torch.int64, device=dev)
+
+    def h(k):
+        m64 = (1 << 64) - 1
+        # splitmix64 on int64 with wrap-around (two's complement == mod 2^64)
+        def c(v):
+            v &= m64
+            return v - (1 << 64) if v >= (1 << 63) else v
+        z = (idx * 8 + k) * 2 + 1
+        z = z * c(0x9E3779B97F4A7C15)
+        z = z ^ c(0xC0FFEE)
+        z = z + c(0x9E3779B97F4A7C15)
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * c(0xBF58476D1CE4E5B9)
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * c(0x94D049BB133111EB)
+        z = z ^ ((z >> 31) & ((1 << 33) - 1))
+        top = (z >> 11) & ((1 << 53) - 1)
+        return top.to(torch.float64) * 1.1102230246251565e-16 + 1.1102230246251565e-16 / 2.0
+    x = torch.floor(200 * h(0) ** 2).to(torch.int32)
+    if name == "poisson":
+        return x, [0.5 + 100 * h(1)]
+    if name == "negative_binomial_mu":
+        return x, [0.5 + 50 * h(1), 0.1 + 100 * h(2)]
+    size = (x + torch.floor(100 * h(1)).to(torch.int32)).to(torch.int32)
+    return x, [size, 0.05 + 0.9 * h(2), 0.01 + 0.49 * h(3)]
+
+
+def run_density(args, mb, torch, dev, rank, world, local_rank, dist_on, barrier):
+    from monty_b200.distributed import density_sum_dev, allreduce_sum
+    n = args.obs
+    x, pars = density_inputs(torch, args.density, n, rank * n, dev)
+    bytes_per_obs = x.element_size() + sum(p.element_size() for p in pars)
+    launches0 = mb._lib.lib.mb200_launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        allreduce_sum(density_sum_dev(args.density, x, pars))
+    torch.cuda.synchronize()
+    barrier()
+    evs = []
+    total = None
+    for _ in range(args.steps):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        part = density_sum_dev(args.density, x, pars)
+        b.record()
+        total = allreduce_sum(part)
+        c.record()
+        evs.append((a, b, c))
+    torch.cuda.synchronize()
+    barrier()
+    clock_info = clocks.stop()
+    launches = mb._lib.lib.mb200_launch_count() - launches0 - 2 * max(args.warmup, 3)
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b, c in evs]))
+    tot_ms = evs[0][0].elapsed_time(evs[-1][2])
+    t = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
+    if dist_on:
+        import torch.distributed as td
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    peak, peak_src = measured_peak()
+    achieved = n * bytes_per_obs / (k_ms * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Gobs/s (log-density %s, f64, fused sum + all-reduce)" % args.density,
+            "value": world * n / (ms_per_step * 1e-3) / 1e9, "unit": "Gobs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "density::%s log-likelihood, %d observations per GPU, reduce-only"
+                                   % (args.density, n), "l2": "inputs %.1f GB >> L2" % (n * bytes_per_obs / 1e9)},
+            "clocks": clock_info, "gpu_launches": int(launches), "log_likelihood": float(total.item()),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "density_kernel<%s>" % args.density, "kernel_ms": k_ms,
+                         "note": "lgamma-heavy: expected FP64-pipe bound, not HBM bound"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +304,11 @@ def main():
     ap.add_argument("--detail", action="store_true", help="also time the other distributions")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="sample", choices=["sample", "density"],
+                    help="density: config C5, fused log-likelihood + all-reduce")
+    ap.add_argument("--density", default="poisson",
+                    choices=["poisson", "negative_binomial_mu", "beta_binomial_prob"])
+    ap.add_argument("--obs", type=int, default=125_000_000, help="observations per GPU (density)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -248,6 +332,13 @@ def main():
         barrier = lambda: td.barrier()  # noqa: E731
     else:
         barrier = lambda: None  # noqa: E731
+
+    if args.workload == "density":
+        run_density(args, mb, torch, dev, rank, world, local_rank, dist_on, barrier)
+        if dist_on:
+            td.barrier()
+            td.destroy_process_group()
+        return
 
     S, D = args.streams, args.draws
     # shard: GPU g holds S streams of the generator seed(42) long-jumped g times

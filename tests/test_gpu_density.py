@@ -122,3 +122,24 @@ def test_device_sum_matches_vector_sum(mb, oracle):
     assert np.allclose(vec[:50000], exp, rtol=1e-13)
     # reproducible run to run
     assert mb.density.log_likelihood("poisson", x, pars) == only
+
+
+def test_device_resident_sum_and_bench_inputs(mb, oracle):
+    """monty_b200.distributed.density_sum_dev on torch tensors, with the C5
+    inputs bench.py generates on the device (same counter hash as the CPU)."""
+    import os, sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from monty_b200.distributed import density_sum_dev
+    dev = torch.device("cuda", 0)
+    n = 200000
+    for name in ("poisson", "negative_binomial_mu", "beta_binomial_prob"):
+        x, pars = bench.density_inputs(torch, name, n, 1000, dev)
+        from oracle_lib import counter_hash
+        idx = np.arange(1000, 1000 + n)
+        assert np.array_equal(x.cpu().numpy(), np.floor(200 * counter_hash(idx, 0) ** 2).astype(np.int32))
+        total = density_sum_dev(name, x, pars).item()
+        ref = oracle.density(name, x.cpu().numpy(), [p.cpu().numpy() for p in pars], True)
+        assert np.isfinite(ref).all()
+        assert abs(total - ref.sum()) <= 1e-11 * abs(ref.sum())
