@@ -142,7 +142,8 @@ def cpu_reference_run(dist, real, n_streams, n_draws, steps, warmup, threads=Non
     from oracle_lib import Oracle, have_reference
     kind = "reference" if have_reference() else "port"
     orc = Oracle(kind)
-    threads = threads or orc.max_threads()
+    # all host cores this process may use (torchrun sets OMP_NUM_THREADS=1, so ask the OS)
+    threads = threads or len(os.sched_getaffinity(0))
     st = orc.seed_states(42, n_streams)
     params = synthetic_params(dist, n_streams)
     times = []

@@ -19,6 +19,7 @@
 
 #include "../../include/monty_b200.h"
 #include "density_dispatch.h"
+#include "deterministic_dispatch.h"
 #include "errors.h"
 #include "jump_poly.h"
 #include "launch_args.h"
@@ -144,6 +145,56 @@ int param_error(mb200_rng* rng, int dist, int real_type, const double* const* pa
   }
   const std::string msg = format_param_error(dist, real_type, v);
   return fail(MB200_ERR_PARAM, rng, "%s", msg.c_str());
+}
+
+// deterministic = TRUE: every sampler returns its expectation and leaves the
+// stream alone (deterministic_kernel.cu).  The values of the streams before
+// the first invalid one are produced, then the reference's error is raised.
+int sample_deterministic(mb200_rng* rng, int dist, int real_type, size_t n_samples,
+                         const double* const* params_host, const size_t* param_len, double* out_host) {
+  const int np = dist_n_params(dist);
+  SampleArgs a{};
+  a.state = rng->d_state;
+  int rc;
+  for (int k = 0; k < np; ++k) {
+    const size_t bytes = param_len[k] * sizeof(double);
+    rc = ensure(rng, reinterpret_cast<void**>(&rng->d_par[k]), &rng->par_cap[k], bytes);
+    if (rc != MB200_OK) return rc;
+    CU(cudaMemcpyAsync(rng->d_par[k], params_host[k], bytes, cudaMemcpyHostToDevice, rng->stream));
+    a.par[k] = rng->d_par[k];
+    a.pstride[k] = param_len[k] == 1 ? 0u : 1u;
+  }
+  const size_t out_bytes = rng->n_streams * n_samples * sizeof(double);
+  rc = ensure(rng, &rng->d_out, &rng->out_cap, out_bytes);
+  if (rc != MB200_OK) return rc;
+  rc = reset_err(rng);
+  if (rc != MB200_OK) return rc;
+  a.out = rng->d_out;
+  a.n_streams = rng->n_streams;
+  a.n_samples = n_samples;
+  a.err = rng->d_err;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CU(launch_deterministic(dist, np, real_type, a, rng->stream));
+  CU(cudaMemcpyAsync(out_host, rng->d_out, out_bytes, cudaMemcpyDeviceToHost, rng->stream));
+  rc = fetch_err(rng);
+  if (rc != MB200_OK) return rc;
+  if (rng->h_err->stream != ~0ull) {
+    if (rng->h_err->code == kErrParam && dist != MB200_DIST_BINOMIAL) {
+      return param_error(rng, dist, real_type, params_host, param_len, false, rng->h_err->stream);
+    }
+    if (rng->h_err->code == kErrHypergeometricDet) {
+      // hypergeometric_deterministic validates and prints the UNROUNDED inputs (%.0f)
+      double v[3];
+      for (int k = 0; k < 3; ++k) v[k] = params_host[k][param_len[k] == 1 ? 0 : rng->h_err->stream];
+      if (real_type == MB200_REAL_F32) for (double& x : v) x = static_cast<float>(x);
+      return fail(MB200_ERR_PARAM, rng, "Invalid call to hypergeometric with n1 = %.0f, n2 = %.0f, k = %.0f",
+                  v[0], v[1], v[2]);
+    }
+    const std::string msg = format_dynamic_error(rng->h_err->code == kErrParam ? kErrInnerBinomial : rng->h_err->code,
+                                                 rng->h_err->vals);
+    return fail(MB200_ERR_PARAM, rng, "%s", msg.c_str());
+  }
+  return MB200_OK;
 }
 
 }  // namespace
@@ -382,13 +433,11 @@ int mb200_rng_sample(mb200_rng* rng, int dist, int real_type, size_t n_samples,
   }
   int rc = check_param_lengths(rng, dist, param_len);
   if (rc != MB200_OK) return rc;
-  if (rng->deterministic) {
-    return fail(MB200_ERR_UNSUPPORTED, rng, "deterministic mode is not implemented yet");
-  }
   if (n_samples == 0) return MB200_OK;
   if (!out_host) return fail(MB200_ERR_ARG, rng, "out_host must not be NULL");
   CU(cudaSetDevice(rng->device));
   if (rng->pending) { rc = mb200_rng_sync(rng); if (rc != MB200_OK) return rc; }
+  if (rng->deterministic) return sample_deterministic(rng, dist, real_type, n_samples, params_host, param_len, out_host);
 
   // stage parameters (R vectors live in host memory)
   SampleArgs a{};
@@ -471,9 +520,6 @@ int mb200_rng_multinomial(mb200_rng* rng, size_t n_samples,
     return fail(MB200_ERR_ARG, rng, "Expected 'prob' to have %d or 1 columns, not %d",
                 (int)rng->n_streams, (int)prob_cols);
   }
-  if (rng->deterministic) {
-    return fail(MB200_ERR_UNSUPPORTED, rng, "deterministic mode is not implemented yet");
-  }
   if (n_samples == 0 || prob_len == 0) return MB200_OK;
   CU(cudaSetDevice(rng->device));
   int rc;
@@ -490,10 +536,17 @@ int mb200_rng_multinomial(mb200_rng* rng, size_t n_samples,
   rc = reset_err(rng);
   if (rc != MB200_OK) return rc;
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  CU(launch_multinomial(rng->d_state, rng->n_streams, n_samples, rng->d_par[0],
-                        size_len == 1 ? 0u : 1u, rng->d_par[1], static_cast<int>(prob_len),
-                        prob_cols == 1 ? 0u : 1u, static_cast<double*>(rng->d_out),
-                        rng->d_err, rng->stream));
+  if (rng->deterministic) {
+    CU(launch_multinomial_deterministic(rng->n_streams, n_samples, rng->d_par[0],
+                                        size_len == 1 ? 0u : 1u, rng->d_par[1], static_cast<int>(prob_len),
+                                        prob_cols == 1 ? 0u : 1u, static_cast<double*>(rng->d_out),
+                                        rng->d_err, rng->stream));
+  } else {
+    CU(launch_multinomial(rng->d_state, rng->n_streams, n_samples, rng->d_par[0],
+                          size_len == 1 ? 0u : 1u, rng->d_par[1], static_cast<int>(prob_len),
+                          prob_cols == 1 ? 0u : 1u, static_cast<double*>(rng->d_out),
+                          rng->d_err, rng->stream));
+  }
   CU(cudaMemcpyAsync(out_host, rng->d_out, out_bytes, cudaMemcpyDeviceToHost, rng->stream));
   rc = fetch_err(rng);
   if (rc != MB200_OK) return rc;

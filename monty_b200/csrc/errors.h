@@ -157,6 +157,10 @@ inline std::string format_dynamic_error(int code, const double* vals) {
              vals[0], vals[1], vals[2]);
   } else if (code == 3) {
     snprintf(buf, sizeof buf, "Invalid call to Poisson with lambda = %g", vals[0]);
+  } else if (code == 4) {   // hdr/cauchy.hpp:21
+    snprintf(buf, sizeof buf, "Can't use Cauchy distribution deterministically; it has no mean");
+  } else if (code == 7) {   // hdr/binomial.hpp:219-221
+    snprintf(buf, sizeof buf, "Invalid call to binomial with n = %f", vals[0]);
   } else {
     snprintf(buf, sizeof buf, "sampler failed with code %d", code);
   }

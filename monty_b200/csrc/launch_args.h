@@ -11,7 +11,11 @@ enum SampleError {
   kErrParam = 1,        // the distribution's own validate() failed
   kErrInnerBinomial = 2,// beta_binomial: binomial_validate on the beta draw
   kErrInnerPoisson = 3, // negative_binomial: poisson_validate on the gamma draw
-  kErrCauchyDeterministic = 4
+  kErrCauchyDeterministic = 4,
+  kErrMultinomialNegative = 5,
+  kErrMultinomialNoPositive = 6,
+  kErrBinomialDetN = 7,      // binomial_deterministic: n < 0 beyond round-off
+  kErrHypergeometricDet = 8  // hypergeometric_deterministic validates the unrounded inputs
 };
 
 // First-offender record written by kernels when a sampler rejects its

@@ -273,3 +273,37 @@ def test_multinomial(mb, oracle, golden):
         mb.monty_random_multinomial(10.0, np.array([0.5, -0.1]), rng)
     with pytest.raises(mb.MontyError, match="No positive prob in call to multinomial"):
         mb.monty_random_multinomial(10.0, np.array([0.0, 0.0]), rng)
+
+
+# ---- deterministic mode (ref: tests/testthat/test-rng.R:675-764, 952-967, ...) ---
+@pytest.mark.parametrize("rt", ["f64", "f32"])
+@pytest.mark.parametrize("name", [n for n in ALL if n != "cauchy"])
+def test_deterministic_mode(mb, golden, oracle, name, rt):
+    """Every sampler returns its expectation and leaves the stream alone
+    (except random_real and the unbounded truncated normal, which draw in the
+    reference too)."""
+    pars = sampler_cases(64)[name]
+    rng = mb.monty_rng_create(64, 20240607, deterministic=True, real_type=rt)
+    before = states_of(mb, rng)
+    y = np.ascontiguousarray(mb.random._sample(rng, name, 5, pars).T)
+    exp = golden["sample/%s/%s/det" % (rt, name)]
+    st = states_of(mb, rng)
+    assert np.array_equal(st, golden["sample/%s/%s/det/state" % (rt, name)])
+    if name not in ("real", "truncated_normal"):
+        assert np.array_equal(st, before)
+    tol = 1e-6 if rt == "f32" else 1e-13
+    assert np.allclose(y, exp, rtol=tol, atol=tol, equal_nan=True), name
+
+
+def test_deterministic_errors(mb):
+    rng = mb.monty_rng_create(2, 1, deterministic=True)
+    with pytest.raises(mb.MontyError, match="Can't use Cauchy distribution deterministically; it has no mean"):
+        mb.monty_random_cauchy(0.0, 1.0, rng)
+    with pytest.raises(mb.MontyError, match=r"Invalid call to binomial with n = -1\.000000"):
+        mb.monty_random_binomial(-1.0, 0.5, rng)
+    with pytest.raises(mb.MontyError, match="Invalid call to binomial with n = 10, p = 1.5, q = -0.5"):
+        mb.monty_random_binomial(10.0, 1.5, rng)
+    assert mb.monty_random_binomial(-1e-10, 0.5, rng)[0] == 0     # round-off in n is forgiven
+    assert np.array_equal(mb.monty_random_n_poisson(3, 2.5, rng), np.full((3, 2), 2.5))
+    y = mb.monty_random_multinomial(10.0, np.array([0.2, 0.3, 0.5]), rng)
+    assert np.allclose(y[:, 0], [2.0, 3.0, 5.0])
