@@ -25,7 +25,7 @@ struct ErrRec {
   unsigned long long stream;   // smallest offending stream index, ~0ull if none
   unsigned long long owner;    // stream that wrote code/vals (== stream when consistent)
   int code;                    // SampleError
-  int pad;
+  unsigned work;               // tile counter of the self-scheduling kernels (starts at ~0u)
   double vals[3];              // values for data-dependent messages
 };
 

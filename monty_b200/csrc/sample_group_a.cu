@@ -3,6 +3,9 @@
 #include "../../include/monty_b200.h"
 #include "sample_dispatch.h"
 #include "sample_kernel.cuh"
+#include "ziggurat_kernel.cuh"
+
+#include <cstdlib>
 
 namespace mb200 {
 template <typename T> using DExpRate = DistExponential<T, false>;
@@ -25,6 +28,11 @@ bool dist_in_group_a(int dist) {
 
 cudaError_t launch_sample_group_a(int dist, int real_type, int out_f32, bool validate_only,
                                   const SampleArgs& a, int sm_count, cudaStream_t st) {
+  if (dist == MB200_DIST_NORMAL_ZIGGURAT && !validate_only && ziggurat_kernel_applies(a)) {
+    // MB200_ZIG_GENERIC=1 keeps the lock-step kernel for A/B measurements
+    static const bool generic = std::getenv("MB200_ZIG_GENERIC") != nullptr;
+    if (!generic) return launch_ziggurat(real_type, out_f32, a, sm_count, st);
+  }
 #define MB200_CASE(id, D) case id: return launch_sample_any<D>(real_type, out_f32, validate_only, a, sm_count, st)
   switch (dist) {
     MB200_CASE(MB200_DIST_REAL, DistReal);

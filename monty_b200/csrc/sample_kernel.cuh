@@ -59,6 +59,7 @@ struct __align__(16) TableSmem {
   double zig_x[264];
   double tail_d[16];
   float tail_f[128];
+  float zig_x2s[260];
 };
 
 __device__ __forceinline__ void report_error(ErrRec* err, unsigned long long stream, int code,
@@ -82,6 +83,10 @@ __device__ __forceinline__ void stage_tables(TableSmem* ts, Ctx& ctx) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) ts->zig_xy[i] = g_zig_xy[i];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) ts->zig_x[i] = g_zig_x[i];
     ctx.zig_xy = ts->zig_xy;
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) {
+      ts->zig_x2s[i] = static_cast<float>(g_zig_x[i] * g_zig_x[i] * 0.72134752044448170368);
+    }
+    ctx.zig_x2s = ts->zig_x2s;
     ctx.zig_xy_saddr = smem_addr(ts->zig_xy);
     ctx.zig_x = ts->zig_x;
   }
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(kBlock)
 validate_kernel(const SampleArgs a) {
   Ctx ctx;
   ctx.err = 0;
-  ctx.zig_xy = g_zig_xy; ctx.zig_xy_saddr = 0; ctx.zig_x = g_zig_x; ctx.tail_d = g_tail_d; ctx.tail_f = g_tail_f;
+  ctx.zig_xy = g_zig_xy; ctx.zig_xy_saddr = 0; ctx.zig_x = g_zig_x; ctx.zig_x2s = nullptr; ctx.tail_d = g_tail_d; ctx.tail_f = g_tail_f;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long stream = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
        stream < a.n_streams; stream += stride) {
