@@ -371,7 +371,8 @@ def main():
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "sample_kernel<%s,%s>" % (args.dist, args.real),
+                "kernel": ("ziggurat_kernel<%s>" % args.real) if (args.dist == "normal_ziggurat" and D >= 2)
+                else "sample_kernel<%s,%s>" % (args.dist, args.real),
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):

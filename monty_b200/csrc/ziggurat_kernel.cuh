@@ -99,6 +99,10 @@ __device__ __noinline__ TailResult<T> ziggurat_tail_from(T u1, X256 state, T x1,
   }
 }
 
+__device__ __forceinline__ uint32_t bump(uint32_t p, uint32_t by) {
+  return __float_as_uint(__fadd_rn(__uint_as_float(p), __uint_as_float(by)));
+}
+
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -186,7 +190,12 @@ __device__ __forceinline__ void zig_word(ZigLane<T, OutT>& L, uint32_t zig_saddr
       wemit = g1 + r * (g0 - g1) < 1.0;
     }
   }
-  if (fast || wemit) L.p += sizeof(OutT);
+  // the slot pointer moves on the FMA pipe (the loop is ALU-pipe bound): a shared
+  // address is below 2^23, so as a float bit pattern it is a subnormal, and
+  // adding the subnormal whose pattern is sizeof(OutT) is exact integer addition
+  // (no flush-to-zero in this translation unit)
+  if (fast) L.p = bump(L.p, sizeof(OutT));
+  if (wemit) L.p = bump(L.p, sizeof(OutT));
   if (park) {
     const float4 w = lds_f32x4(wtab_lane_saddr + (idx >> 3));
     const float zr = __fmaf_rn(m, w.z, w.w);
@@ -247,7 +256,10 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
 #pragma unroll
     for (int t = 0; t < STEPS; ++t) {
       const uint32_t r = rsub + t * RPI;
-      roff[t] = r * n - (((sm + r) * nm) & 31u) + sub;
+      roff[t] = (r * n - (((sm + r) * nm) & 31u) + sub) * static_cast<uint32_t>(sizeof(OutT));   // bytes
+      // opaque: keeps the 16 offsets in registers instead of re-deriving them
+      // (6 ALU instructions each) at every window
+      asm volatile("" : "+r"(roff[t]));
     }
 
     ZigLane<T, OutT> L;
@@ -284,7 +296,7 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
       if (vec_ok && n_hot == kTile) {
         // every row is full: STEPS x (RPI rows x 256 B / 128 B), loads batched before stores
         constexpr int HALF = STEPS / 2;
-        OutT* const wwin = wbase + wpos;
+        char* const wwin = reinterpret_cast<char*>(wbase + wpos);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           V v[HALF];
@@ -293,7 +305,7 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
             v[t] = lds_vec(rd_saddr + static_cast<uint32_t>((h * HALF + t) * RPI * PITCH * sizeof(OutT)), OutT());
           }
 #pragma unroll
-          for (int t = 0; t < HALF; ++t) *reinterpret_cast<V*>(wwin + roff[h * HALF + t]) = v[t];
+          for (int t = 0; t < HALF; ++t) *reinterpret_cast<V*>(wwin + roff[h * HALF + t]) = v[t];   // 64-bit base + 32-bit offset
         }
       } else {
         // ragged window: lane e of step r writes element e of row r if it belongs to the row
