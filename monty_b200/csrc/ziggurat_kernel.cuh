@@ -34,6 +34,8 @@
 // scheme of sample_kernel.cuh; the tile is filled with scalar stores through a
 // per-lane pointer that advances on every emitted draw.
 #pragma once
+#include <cstdlib>
+
 #include "sample_kernel.cuh"
 
 namespace mb200 {
@@ -344,7 +346,12 @@ template <typename T, typename OutT>
 cudaError_t launch_ziggurat_t(const SampleArgs& a, int sm_count, cudaStream_t st) {
   const unsigned long long n_tiles = (a.n_streams + 31) / 32;
   unsigned long long wpb = (n_tiles + sm_count - 1) / sm_count;      // spread small problems over the SMs
-  if (wpb > kZigMaxWarps) wpb = kZigMaxWarps;
+  unsigned long long max_warps = kZigMaxWarps;
+  if (const char* w = std::getenv("MB200_ZIG_WARPS")) {       // occupancy experiments
+    const long v = std::atol(w);
+    if (v >= 1 && v <= kZigMaxWarps) max_warps = static_cast<unsigned long long>(v);
+  }
+  if (wpb > max_warps) wpb = max_warps;
   if (wpb < 1) wpb = 1;
   unsigned long long grid = (n_tiles + wpb - 1) / wpb;
   if (grid > static_cast<unsigned long long>(sm_count)) grid = sm_count;
