@@ -3,6 +3,7 @@
 #include "../../include/monty_b200.h"
 #include "sample_dispatch.h"
 #include "sample_kernel.cuh"
+#include "sorted_kernel.cuh"
 
 namespace mb200 {
 template <typename T> using DGammaScale = DistGamma<T, false>;
@@ -23,7 +24,7 @@ bool dist_in_group_b(int dist) {
 
 cudaError_t launch_sample_group_b(int dist, int real_type, int out_f32, bool validate_only,
                                   const SampleArgs& a, int sm_count, cudaStream_t st) {
-#define MB200_CASE(id, D) case id: return launch_sample_any<D>(real_type, out_f32, validate_only, a, sm_count, st)
+#define MB200_CASE(id, D) case id: return launch_sample_regimes<D>(real_type, out_f32, validate_only, a, sm_count, st)
   switch (dist) {
     MB200_CASE(MB200_DIST_BINOMIAL, DistBinomial);
     MB200_CASE(MB200_DIST_POISSON, DistPoisson);

@@ -1,0 +1,219 @@
+// sorted_kernel.cuh -- samplers whose cost depends on the REGIME their
+// per-stream parameters select (binomial: constant / inversion / BTRS;
+// Poisson: Knuth / Hormann / Cauchy; gamma: small / exponential / large;
+// hypergeometric: HIN / H2PE; ...), for short batches (n_samples <= 16: the
+// dust2 SIR-step shape, BASELINE configs[2] and [3]).
+//
+// In the generic kernel a warp holds 32 consecutive streams, so with
+// per-stream parameters spanning the regimes every warp executes every regime
+// one after the other: ncu shows 4-10 active lanes per instruction
+// (profiles/r01_binomial_d1_ncu_summary.txt, r01_hypergeometric_...).  Here a
+// CTA takes a tile of 512 consecutive streams and
+//   1. classifies each stream from its parameters alone (D::regime(), a few
+//      compares -- none of the set-up work),
+//   2. counting-sorts the tile by regime in shared memory (ballot-free:
+//      shared atomics hand out ranks; the order inside a regime is irrelevant
+//      because a stream's draws depend only on its own state and parameters),
+//   3. lets thread t process the t-th stream OF THE SORTED ORDER: warps are
+//      regime-pure except at the <= R-1 boundaries of a tile, so prepare() and
+//      draw() run without regime divergence (rejection-loop trip counts still
+//      vary inside a warp),
+//   4. stages the draws in shared memory and writes the tile's contiguous
+//      output range [first_stream * n, (first_stream + 512) * n) coalesced.
+// Generator states are read and written in place (one 32-byte sector per
+// stream, whichever thread handles it).  Results are bit-identical to the
+// generic kernel's: only the assignment of streams to lanes changes.
+#pragma once
+#include <cstdlib>
+
+#include "sample_kernel.cuh"
+
+namespace mb200 {
+
+constexpr int kSortBlock = 256;
+constexpr int kSortTile = 512;            // streams per tile, kSortTile / kSortBlock per thread
+constexpr int kSortMaxSamples = 16;
+constexpr int kSortKeys = 16;             // regime keys 0..14, 15 = stream does not exist
+
+template <typename OutT>
+inline size_t sorted_smem_bytes(int n_params, unsigned n_samples, int tables) {
+  const unsigned pitch = n_samples | 1u;                                // odd: bank spread
+  size_t b = sizeof(OutT) * kSortTile * pitch;
+  b = (b + 15) & ~static_cast<size_t>(15);
+  b += sizeof(double) * kSortTile * (n_params > 0 ? n_params : 1);
+  if (tables != kNoTables) b += sizeof(TableSmem);
+  return b;
+}
+
+template <class D, typename T, typename OutT>
+__global__ void __launch_bounds__(kSortBlock, 2)
+sorted_sample_kernel(const SampleArgs a) {
+  constexpr int NP = D::NP;
+  constexpr int PER = kSortTile / kSortBlock;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned s_count[kSortKeys];
+  __shared__ unsigned s_offset[kSortKeys];
+  __shared__ unsigned short s_order[kSortTile];
+
+  const unsigned n = static_cast<unsigned>(a.n_samples);
+  const unsigned pitch = n | 1u;
+  OutT* out_s = reinterpret_cast<OutT*>(smem_raw);
+  size_t off = (sizeof(OutT) * kSortTile * pitch + 15) & ~static_cast<size_t>(15);
+  double* par_s = reinterpret_cast<double*>(smem_raw + off);
+  off += sizeof(double) * kSortTile * (NP > 0 ? NP : 1);
+  TableSmem* ts = reinterpret_cast<TableSmem*>(smem_raw + off);
+
+  Ctx ctx;
+  ctx.err = 0;
+  stage_tables<D::TABLES>(ts, ctx);
+
+  const unsigned tid = threadIdx.x;
+  OutT* const out = static_cast<OutT*>(a.out);
+  const unsigned long long n_streams = a.n_streams;
+  const unsigned long long n_tiles = (n_streams + kSortTile - 1) / kSortTile;
+
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long base = tile * kSortTile;
+    const unsigned count = (n_streams - base) < kSortTile ? static_cast<unsigned>(n_streams - base) : kSortTile;
+    if (tid < kSortKeys) s_count[tid] = 0;
+    __syncthreads();
+    // 1. parameters -> shared memory, regime key and rank inside the key
+    unsigned key[PER], rank[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const unsigned j = tid + i * kSortBlock;
+      key[i] = kSortKeys - 1;
+      if (j < count) {
+        T par[NP > 0 ? NP : 1];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          const double v = a.par[k][a.pstride[k] ? base + j : 0];
+          par_s[k * kSortTile + j] = v;
+          par[k] = static_cast<T>(v);
+        }
+        const int r = D::regime(par);
+        key[i] = static_cast<unsigned>(r < 0 ? 0 : (r > kSortKeys - 2 ? kSortKeys - 2 : r));
+      }
+      rank[i] = atomicAdd(&s_count[key[i]], 1u);
+    }
+    __syncthreads();
+    // 2. exclusive scan of the 16 counts (one warp), then the sorted order
+    if (tid < 32) {
+      const unsigned c = tid < kSortKeys ? s_count[tid] : 0;
+      unsigned incl = c;
+#pragma unroll
+      for (int d = 1; d < kSortKeys; d <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (tid >= static_cast<unsigned>(d)) incl += up;
+      }
+      if (tid < kSortKeys) s_offset[tid] = incl - c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      s_order[s_offset[key[i]] + rank[i]] = static_cast<unsigned short>(tid + i * kSortBlock);
+    }
+    __syncthreads();
+    // 3. thread t draws for the t-th stream of the sorted order
+#pragma unroll 1
+    for (int i = 0; i < PER; ++i) {
+      const unsigned slot = tid + i * kSortBlock;
+      if (slot >= count) continue;                 // the non-existent streams sort last
+      const unsigned j = s_order[slot];
+      const unsigned long long stream = base + j;
+      T par[NP > 0 ? NP : 1];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) par[k] = static_cast<T>(par_s[k * kSortTile + j]);
+      typename D::Prep prep;
+      OutT* row = out_s + j * pitch;
+      const int e = D::prepare(par, prep, ctx);
+      if (e != kOk) {
+        report_error(a.err, stream, e, nullptr);
+        for (unsigned d = 0; d < n; ++d) row[d] = out_nan<OutT>();
+        continue;
+      }
+      Rng rng;
+      rng.s = load_state(a.state, stream);
+      bool live = true;
+#pragma unroll 1
+      for (unsigned d = 0; d < n; ++d) {
+        OutT y = out_nan<OutT>();
+        if (live) {
+          y = static_cast<OutT>(D::draw(rng, prep, ctx));
+          if (D::DYN_ERR && ctx.err) {
+            // a data-dependent failure inside a composition: the stream is
+            // abandoned and the rest of its output is NaN (as in sample_kernel)
+            report_error(a.err, stream, ctx.err, ctx.err_vals);
+            ctx.err = 0;
+            live = false;
+            y = out_nan<OutT>();
+          }
+        }
+        row[d] = y;
+      }
+      store_state(a.state, stream, rng.s);
+    }
+    __syncthreads();
+    // 4. the tile's output range is contiguous: coalesced copy out
+    OutT* const dst = out + base * n;
+    const unsigned total = count * n;
+    if (n == 1) {
+      for (unsigned e = tid; e < total; e += kSortBlock) dst[e] = out_s[e * pitch];
+    } else {
+      unsigned r = tid / n, c = tid - r * n;       // element e = r * n + c, advanced by kSortBlock
+      const unsigned dr = kSortBlock / n, dc = kSortBlock - dr * n;
+      for (unsigned e = tid; e < total; e += kSortBlock) {
+        dst[e] = out_s[r * pitch + c];
+        r += dr; c += dc;
+        if (c >= n) { c -= n; ++r; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <class D, typename T, typename OutT>
+cudaError_t launch_sorted_t(const SampleArgs& a, int sm_count, cudaStream_t st) {
+  const size_t smem = sorted_smem_bytes<OutT>(D::NP, static_cast<unsigned>(a.n_samples), D::TABLES);
+  cudaError_t e = cudaFuncSetAttribute(sorted_sample_kernel<D, T, OutT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  const unsigned long long tiles = (a.n_streams + kSortTile - 1) / kSortTile;
+  const unsigned long long cap = static_cast<unsigned long long>(sm_count) * 8;
+  const unsigned grid = static_cast<unsigned>(tiles < cap ? (tiles ? tiles : 1) : cap);
+  sorted_sample_kernel<D, T, OutT><<<grid, kSortBlock, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+// Is the sorted kernel the right one for this launch?  Only when the
+// parameters vary per stream (with scalars every stream is in the same regime
+// already), the batch is short enough to stage, and the tile is worth sorting.
+template <class D>
+inline bool sorted_kernel_applies(const SampleArgs& a) {
+  if (D::REGIMES <= 1 || a.n_samples < 1 || a.n_samples > kSortMaxSamples) return false;
+  if (a.n_streams < 4 * kSortTile) return false;
+  bool any_vector = false;
+  for (int k = 0; k < D::NP; ++k) any_vector = any_vector || a.pstride[k] != 0;
+  return any_vector;
+}
+
+// Front end used by the sampler groups: the sorted kernel where it applies
+// (MB200_NO_SORT=1 keeps the generic kernel, for A/B measurements), else the
+// generic one.
+template <template <typename> class D>
+cudaError_t launch_sample_regimes(int real_type, int out_f32, bool validate_only,
+                                  const SampleArgs& a, int sm_count, cudaStream_t st) {
+  if constexpr (D<double>::REGIMES > 1) {
+    static const bool no_sort = std::getenv("MB200_NO_SORT") != nullptr;
+    if (!validate_only && !no_sort && sorted_kernel_applies<D<double>>(a)) {
+      if (real_type == 1) {
+        return out_f32 ? launch_sorted_t<D<float>, float, float>(a, sm_count, st)
+                       : launch_sorted_t<D<float>, float, double>(a, sm_count, st);
+      }
+      return launch_sorted_t<D<double>, double, double>(a, sm_count, st);
+    }
+  }
+  return launch_sample_any<D>(real_type, out_f32, validate_only, a, sm_count, st);
+}
+
+}  // namespace mb200

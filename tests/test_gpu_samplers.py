@@ -76,6 +76,37 @@ def test_double_parity(mb, oracle, name, shape):
         assert not bad.any(), (name, np.abs(y - exp)[bad][:3], exp[bad][:3])
 
 
+SORTED = ["binomial", "poisson", "gamma_scale", "gamma_rate", "beta", "negative_binomial_prob",
+          "negative_binomial_mu", "hypergeometric", "truncated_normal"]
+
+
+@pytest.mark.parametrize("name", SORTED)
+@pytest.mark.parametrize("shape", [(5000, 1), (4096, 16), (70001, 7), (2048, 2)])
+def test_regime_sorted_kernel_parity(mb, oracle, name, shape):
+    """Per-stream parameters, n_samples <= 16, >= 2048 streams: the regime-
+    sorting kernel (csrc/sorted_kernel.cuh).  Same bars as test_double_parity;
+    shapes cover a ragged last tile, n_samples = 1 and odd n_samples."""
+    n, ns = shape
+    pars = sampler_cases(n)[name]
+    y, st, _ = gpu_sample(mb, name, n, ns, pars)
+    ost = oracle.seed_states(7, n)
+    exp = oracle.sample(name, ost, ns, pars)
+    assert np.array_equal(st, ost), "final generator states differ"
+    if name in INTEGER_VALUED:
+        assert np.mean(y != exp) == 0.0
+    else:
+        loc = 0.0
+        if name == "truncated_normal":
+            loc = (np.abs(np.broadcast_to(np.atleast_1d(pars[0]), (n,)))
+                   + 6 * np.abs(np.broadcast_to(np.atleast_1d(pars[1]), (n,))))[:, None]
+        # gamma-family draws assemble (1 + c x)^3 from a normal that may differ
+        # by 3 ulp: 16 eps for all but a vanishing fraction, 256 eps for every draw
+        err = np.abs(y - exp)
+        scale = np.finfo(np.float64).eps * (np.abs(exp) + loc + 1e-300)
+        assert np.mean(err <= 16 * scale) > 0.9999, name
+        assert (err <= 256 * scale).all(), (name, (err / scale).max())
+
+
 @pytest.mark.parametrize("name", sorted(standard_cases(4)))
 def test_double_continuous_within_4_ulp(mb, oracle, name):
     n, ns = 2048, 64
