@@ -1,0 +1,40 @@
+/* examples.h -- C entry points of monty_b200/libmonty_b200_examples.so:
+ * consumers of the device-side monty::random API (include/monty_b200/random.cuh)
+ * written the way dust2 / odin2 models consume the reference's headers. */
+#ifndef MONTY_B200_EXAMPLES_H
+#define MONTY_B200_EXAMPLES_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../include/monty_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One inline draw per stream of distribution `dist` (MB200_DIST_*) through
+ * monty::random::<dist><real_type>(state, params...): the same draws as
+ * mb200_rng_sample(..., n_samples = 1, ...).  params_host[k] has length 1 or
+ * n_streams.  out_host receives n_streams doubles. */
+int mb200_example_inline_draw(mb200_rng* rng, int dist, int real_type,
+                              const double* const* params_host, const size_t* param_len,
+                              double* out_host);
+
+/* Bootstrap particle filter of the stochastic SIR model of the reference's
+ * test-suite (tests/testthat/helper-sir-filter.R:56-117): n_particles =
+ * n_streams of `system`, one stream in `filter` for the systematic
+ * resampling.  Between observations every particle runs its dt = 1 steps in
+ * registers: two binomial draws per step, then the exponential observation
+ * noise and the Poisson log-density, fused in one kernel.
+ * data_time/data_incidence: n_data observations (times are integers, increasing).
+ * final_state_host: optional, 4 x n_particles doubles (S, I, R, cases per particle).
+ * resample = 0 skips the resampling (trajectory parity tests). */
+int mb200_example_sir_filter(mb200_rng* system, mb200_rng* filter,
+                             double N, double I0, double beta, double gamma, double exp_noise,
+                             const double* data_time, const double* data_incidence, size_t n_data,
+                             int resample, double* log_likelihood, double* final_state_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

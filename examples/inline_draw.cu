@@ -1,0 +1,100 @@
+// inline_draw.cu -- every sampler of the device-side monty::random API
+// (include/monty_b200/random.cuh) called the way a model's update() calls it:
+// one draw per stream, state loaded into registers, drawn from, stored back.
+// Used by tests/test_gpu_facade.py to prove that the inline API produces the
+// draws of the bulk C-ABI path (which the oracle tests pin to the reference).
+#include <cuda_runtime.h>
+
+#include "../include/monty_b200/random.cuh"
+#include "examples.h"
+
+namespace {
+
+struct InlineArgs {
+  uint64_t* states;
+  size_t n;
+  const double* par[4];
+  unsigned stride[4];
+  double* out;
+  int dist;
+};
+
+template <typename T>
+__global__ void inline_draw_kernel(const InlineArgs a) {
+  namespace mr = monty::random;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= a.n) return;
+  T p[4];
+  for (int k = 0; k < 4; ++k) p[k] = a.par[k] ? static_cast<T>(a.par[k][a.stride[k] ? i : 0]) : T(0);
+  auto g = mr::load_state(a.states, i);
+  T v;
+  switch (a.dist) {
+  case MB200_DIST_REAL: v = mr::random_real<T>(g); break;
+  case MB200_DIST_UNIFORM: v = mr::uniform<T>(g, p[0], p[1]); break;
+  case MB200_DIST_EXPONENTIAL_RATE: v = mr::exponential_rate<T>(g, p[0]); break;
+  case MB200_DIST_EXPONENTIAL_MEAN: v = mr::exponential_mean<T>(g, p[0]); break;
+  case MB200_DIST_NORMAL_BOX_MULLER: v = mr::normal<T>(g, p[0], p[1]); break;
+  case MB200_DIST_NORMAL_POLAR: v = mr::normal<T, mr::algorithm::normal::polar>(g, p[0], p[1]); break;
+  case MB200_DIST_NORMAL_ZIGGURAT: v = mr::normal<T, mr::algorithm::normal::ziggurat>(g, p[0], p[1]); break;
+  case MB200_DIST_BINOMIAL: v = mr::binomial<T>(g, p[0], p[1]); break;
+  case MB200_DIST_POISSON: v = mr::poisson<T>(g, p[0]); break;
+  case MB200_DIST_GAMMA_SCALE: v = mr::gamma_scale<T>(g, p[0], p[1]); break;
+  case MB200_DIST_GAMMA_RATE: v = mr::gamma_rate<T>(g, p[0], p[1]); break;
+  case MB200_DIST_BETA: v = mr::beta<T>(g, p[0], p[1]); break;
+  case MB200_DIST_NEGATIVE_BINOMIAL_PROB: v = mr::negative_binomial_prob<T>(g, p[0], p[1]); break;
+  case MB200_DIST_NEGATIVE_BINOMIAL_MU: v = mr::negative_binomial_mu<T>(g, p[0], p[1]); break;
+  case MB200_DIST_HYPERGEOMETRIC: v = mr::hypergeometric<T>(g, p[0], p[1], p[2]); break;
+  case MB200_DIST_TRUNCATED_NORMAL: v = mr::truncated_normal<T>(g, p[0], p[1], p[2], p[3]); break;
+  case MB200_DIST_CAUCHY: v = mr::cauchy<T>(g, p[0], p[1]); break;
+  case MB200_DIST_WEIBULL: v = mr::weibull<T>(g, p[0], p[1]); break;
+  case MB200_DIST_LOG_NORMAL: v = mr::log_normal<T>(g, p[0], p[1]); break;
+  case MB200_DIST_BETA_BINOMIAL_PROB: v = mr::beta_binomial_prob<T>(g, p[0], p[1], p[2]); break;
+  case MB200_DIST_BETA_BINOMIAL_AB: v = mr::beta_binomial_ab<T>(g, p[0], p[1], p[2]); break;
+  case MB200_DIST_ZI_POISSON: v = mr::zi_poisson<T>(g, p[0], p[1]); break;
+  case MB200_DIST_ZI_NEGATIVE_BINOMIAL_PROB: v = mr::zi_negative_binomial_prob<T>(g, p[0], p[1], p[2]); break;
+  case MB200_DIST_ZI_NEGATIVE_BINOMIAL_MU: v = mr::zi_negative_binomial_mu<T>(g, p[0], p[1], p[2]); break;
+  default: v = 0; break;
+  }
+  mr::store_state(a.states, i, g);
+  a.out[i] = static_cast<double>(v);
+}
+
+}  // namespace
+
+extern "C" int mb200_example_inline_draw(mb200_rng* rng, int dist, int real_type,
+                                         const double* const* params_host, const size_t* param_len,
+                                         double* out_host) {
+  if (!rng || !out_host) return MB200_ERR_ARG;
+  if (cudaSetDevice(mb200_rng_device(rng)) != cudaSuccess) return MB200_ERR_CUDA;
+  if (mb200_rng_sync(rng) != MB200_OK) return MB200_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(mb200_rng_cuda_stream(rng));
+  InlineArgs a{};
+  a.states = mb200_rng_state_dev(rng);
+  a.n = mb200_rng_n_streams(rng);
+  a.dist = dist;
+  double* d_par[4] = {nullptr, nullptr, nullptr, nullptr};
+  int rc = MB200_OK;
+  for (int k = 0; k < 4 && rc == MB200_OK; ++k) {
+    if (!params_host || !params_host[k] || param_len[k] == 0) continue;
+    if (cudaMalloc(&d_par[k], param_len[k] * sizeof(double)) != cudaSuccess ||
+        cudaMemcpyAsync(d_par[k], params_host[k], param_len[k] * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      rc = MB200_ERR_CUDA;
+    }
+    a.par[k] = d_par[k];
+    a.stride[k] = param_len[k] == 1 ? 0u : 1u;
+  }
+  if (rc == MB200_OK && cudaMalloc(&a.out, a.n * sizeof(double)) != cudaSuccess) rc = MB200_ERR_CUDA;
+  if (rc == MB200_OK) {
+    const unsigned block = 128, grid = static_cast<unsigned>((a.n + block - 1) / block);
+    if (real_type == MB200_REAL_F32) inline_draw_kernel<float><<<grid, block, 0, st>>>(a);
+    else inline_draw_kernel<double><<<grid, block, 0, st>>>(a);
+    if (cudaGetLastError() != cudaSuccess ||
+        cudaMemcpyAsync(out_host, a.out, a.n * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = MB200_ERR_CUDA;
+    }
+  }
+  for (double* p : d_par) if (p) cudaFree(p);
+  if (a.out) cudaFree(a.out);
+  return rc;
+}

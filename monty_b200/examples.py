@@ -1,0 +1,47 @@
+"""ctypes binding of monty_b200/libmonty_b200_examples.so: consumers of the
+device-side monty::random API (include/monty_b200/random.cuh), see
+examples/examples.h.  Like the main library there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._lib import DIST, check, lib as _main  # noqa: F401  (loads libmonty_b200.so first)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmonty_b200_examples.so")
+if not os.path.exists(LIB_PATH):
+    raise ImportError("%s is missing: build it with `python __graft_entry__.py`" % LIB_PATH)
+lib = C.CDLL(LIB_PATH)
+lib.mb200_example_inline_draw.restype = C.c_int
+lib.mb200_example_sir_filter.restype = C.c_int
+
+
+def inline_draw(state, dist, params=()):
+    """One draw per stream through monty::random::<dist>() inside a kernel."""
+    arrs = [np.ascontiguousarray(np.atleast_1d(np.asarray(p, dtype=np.float64))) for p in params]
+    ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs] + [None] * (4 - len(arrs)))
+    lens = (C.c_size_t * 4)(*[a.size for a in arrs] + [0] * (4 - len(arrs)))
+    out = np.empty(state.n_streams, dtype=np.float64)
+    check(lib.mb200_example_inline_draw(state.handle, C.c_int(DIST[dist]),
+                                        C.c_int(1 if state.real_type == "f32" else 0),
+                                        ptrs, lens, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def sir_filter(system, filt, pars, data_time, data_incidence, resample=True, return_state=False):
+    """Bootstrap particle filter of the SIR model of the reference's test-suite
+    (tests/testthat/helper-sir-filter.R): `system` has one stream per particle,
+    `filt` one stream.  pars: dict(N, I0, beta, gamma, exp_noise)."""
+    t = np.ascontiguousarray(data_time, dtype=np.float64)
+    y = np.ascontiguousarray(data_incidence, dtype=np.float64)
+    ll = C.c_double(0.0)
+    n = system.n_streams
+    final = np.empty((4, n), dtype=np.float64) if return_state else None
+    check(lib.mb200_example_sir_filter(
+        system.handle, filt.handle, C.c_double(pars["N"]), C.c_double(pars["I0"]),
+        C.c_double(pars["beta"]), C.c_double(pars["gamma"]), C.c_double(pars["exp_noise"]),
+        t.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_size_t(t.size),
+        C.c_int(1 if resample else 0), C.byref(ll),
+        final.ctypes.data_as(C.c_void_p) if final is not None else None))
+    return (ll.value, final) if return_state else ll.value

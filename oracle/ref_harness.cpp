@@ -18,6 +18,7 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may load the resulting library.  The product
 // (monty_b200/) never does.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -399,6 +400,76 @@ void ref_tables(double* zig_x /*257*/, double* zig_y /*256*/,
   for (int i = 0; i < 256; ++i) zig_y[i] = mr::ziggurat::y[i];
   for (int i = 0; i < 128; ++i) tail_f[i] = mr::k_tail_values_f[i];
   for (int i = 0; i < 10; ++i) tail_d[i] = mr::k_tail_values_d[i];
+}
+
+// The stochastic SIR model and bootstrap particle filter of the reference's
+// own test-suite (tests/testthat/helper-sir-filter.R:56-117, an R script),
+// restated over the reference's C++ samplers and densities: per particle two
+// binomial draws per step, an exponential observation noise and a Poisson
+// log-density per observation; systematic resampling with one uniform from
+// the filter stream (dust_resample_weight, :113-117).  Checker for
+// examples/sir_filter.cu.
+int ref_sir_filter(uint64_t* system_state, size_t n, uint64_t* filter_state,
+                   double N, double I0, double beta, double gamma, double exp_noise,
+                   const double* data_time, const double* data_incidence, size_t n_data,
+                   int resample, double* ll_out, double* final_state /* [4][n] */) {
+  try {
+    std::vector<rng256p> sys, fil;
+    load_states(system_state, n, false, sys);
+    load_states(filter_state, 1, false, fil);
+    std::vector<double> S(n, N - I0), I(n, I0), R(n, 0.0), cases(n, 0.0), logw(n), w(n), cum(n);
+    std::vector<double> S2(n), I2(n), R2(n), C2(n);
+    const double dt = 1;
+    double time = 0, ll = 0;
+    for (size_t d = 0; d < n_data; ++d) {
+      const double to = data_time[d];
+      for (size_t i = 0; i < n; ++i) {
+        for (double t = time + dt; t <= to; t += dt) {                    // sir_run / sir_step
+          const double p_SI = 1 - std::exp(-beta * I[i] / N * dt);
+          const double p_IR = 1 - std::exp(-gamma * dt);
+          const double n_SI = mr::binomial<double>(sys[i], S[i], p_SI);
+          const double n_IR = mr::binomial<double>(sys[i], I[i], p_IR);
+          const double carried = std::fmod(t, 1.0) == 0 ? 0 : cases[i];
+          S[i] = S[i] - n_SI;
+          I[i] = I[i] + n_SI - n_IR;
+          R[i] = R[i] + n_IR;
+          cases[i] = carried + n_SI;
+        }
+        const double noise = mr::exponential_rate<double>(sys[i], exp_noise);
+        logw[i] = md::poisson(data_incidence[d], cases[i] + noise, true);
+      }
+      double m = -INFINITY, total = 0;
+      for (size_t i = 0; i < n; ++i) m = std::max(m, logw[i]);
+      for (size_t i = 0; i < n; ++i) { w[i] = std::exp(logw[i] - m); total += w[i]; }
+      ll += std::log(total / static_cast<double>(n)) + m;
+      const double u = mr::random_real<double>(fil[0]);
+      if (resample) {
+        double run = 0;
+        for (size_t i = 0; i < n; ++i) { run += w[i] / total; cum[i] = run; }
+        const double nn = static_cast<double>(n);
+        for (size_t j = 0; j < n; ++j) {
+          const double x = u / nn + static_cast<double>(j) * (1 / nn);
+          size_t k = std::upper_bound(cum.begin(), cum.end(), x) - cum.begin();   // findInterval
+          if (k >= n) k = n - 1;
+          S2[j] = S[k]; I2[j] = I[k]; R2[j] = R[k]; C2[j] = cases[k];
+        }
+        S.swap(S2); I.swap(I2); R.swap(R2); cases.swap(C2);
+      }
+      time = to;
+    }
+    store_states(sys, system_state);
+    store_states(fil, filter_state);
+    *ll_out = ll;
+    if (final_state) {
+      for (size_t i = 0; i < n; ++i) {
+        final_state[i] = S[i]; final_state[n + i] = I[i]; final_state[2 * n + i] = R[i]; final_state[3 * n + i] = cases[i];
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
 }
 
 }  // extern "C"

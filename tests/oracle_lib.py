@@ -158,6 +158,26 @@ class Oracle:
             raise OracleError(self._err())
         return out
 
+    def sir_filter(self, system_state, filter_state, pars, data_time, data_incidence, resample=True):
+        """The SIR particle filter of the reference's test-suite over the
+        reference's C++ samplers (oracle/ref_harness.cpp, reference kind only).
+        States advanced in place; returns (log_likelihood, final [4][n])."""
+        assert self.kind == "reference"
+        n = system_state.shape[0]
+        t = np.ascontiguousarray(data_time, dtype=np.float64)
+        y = np.ascontiguousarray(data_incidence, dtype=np.float64)
+        ll = C.c_double(0.0)
+        final = np.empty((4, n), dtype=np.float64)
+        rc = self.lib.ref_sir_filter(
+            system_state.ctypes.data_as(C.c_void_p), C.c_size_t(n),
+            filter_state.ctypes.data_as(C.c_void_p), C.c_double(pars["N"]), C.c_double(pars["I0"]),
+            C.c_double(pars["beta"]), C.c_double(pars["gamma"]), C.c_double(pars["exp_noise"]),
+            t.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), C.c_size_t(t.size),
+            C.c_int(1 if resample else 0), C.byref(ll), final.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise OracleError(self._err())
+        return ll.value, final
+
     def multinomial(self, state, n_samples, size, prob, deterministic=False):
         n_streams = state.shape[0]
         size = np.ascontiguousarray(np.atleast_1d(size), dtype=np.float64)

@@ -72,3 +72,33 @@ def test_product_does_not_reference_the_oracle():
                 if re.search(r"oracle_lib|libmonty_oracle|libmonty_ref|oracle/", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_examples_library_and_host_headers():
+    """The consumers of the device-side API build into their own library; the
+    host prng class compiles as plain C++ against the C-ABI header."""
+    import subprocess
+    ex_header = os.path.join(ROOT, "examples", "examples.h")
+    ex_lib = os.path.join(ROOT, "monty_b200", "libmonty_b200_examples.so")
+    assert os.path.exists(ex_lib), "build it: make -C monty_b200/csrc"
+    ctypes.CDLL(LIB, mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(ex_lib)
+    for name in re.findall(r"\b(mb200_example_[a-z0-9_]+)\s*\(", open(ex_header).read()):
+        assert hasattr(lib, name), name
+    src = '#include "include/monty_b200/prng.hpp"\nint main() { return sizeof(monty_b200::prng) ? 0 : 1; }\n'
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", ROOT, "-"],
+                       input=src, text=True, capture_output=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+
+
+def test_device_facade_declares_the_reference_names():
+    """include/monty_b200/random.cuh mirrors the C++ names odin2 generates
+    (reference R/dsl-distributions.R:57-340)."""
+    txt = open(os.path.join(ROOT, "include", "monty_b200", "random.cuh")).read()
+    for name in ("uniform", "exponential_rate", "exponential_mean", "binomial", "poisson", "gamma_scale",
+                 "gamma_rate", "beta", "negative_binomial_prob", "negative_binomial_mu", "hypergeometric",
+                 "truncated_normal", "cauchy", "weibull", "log_normal", "beta_binomial_prob",
+                 "beta_binomial_ab", "zi_poisson", "zi_negative_binomial_prob", "zi_negative_binomial_mu"):
+        assert re.search(r"MONTY_B200_SAMPLER\(%s," % name, txt), name
+    for name in ("random_real", "random_normal", "normal", "seed", "jump", "long_jump", "generator"):
+        assert re.search(r"\b%s\b" % name, txt), name
