@@ -44,7 +44,7 @@ __device__ __forceinline__ void store_state(uint64_t* __restrict__ state, size_t
 //   s3' = rotl(s3 ^ s1, 45) = swap halves, then rotate left by 13
 // The 64-bit formulation made ptxas spend 5 more ALU ops per step on the
 // rotate and on two-input xors; the uniform kernel is ALU-pipe bound, so this
-// is worth 25% of its throughput (profiles/r01_*).
+// is worth 25% of its throughput (profiles/r01_baseline_*_details.csv).
 __device__ __forceinline__ void x256_step(X256& s) {
   const uint32_t s0l = static_cast<uint32_t>(s.s0), s0h = static_cast<uint32_t>(s.s0 >> 32);
   const uint32_t s1l = static_cast<uint32_t>(s.s1), s1h = static_cast<uint32_t>(s.s1 >> 32);

@@ -10,7 +10,7 @@
 // warp-iterations), the random {x, y} look-up is an 8-byte-per-bank-group
 // gather that costs ~10 shared-memory wavefronts per warp-draw, and the budget
 // at the HBM roofline is only 48 issue cycles and 12 shared-memory wavefronts
-// per warp-draw (profiles/r01_zig_*.txt).  This kernel is built around those
+// per warp-draw (profiles/r01_ziggurat_*.txt).  This kernel is built around those
 // three numbers:
 //
 //  * One word per lane per iteration, no data-dependent branch.  A lane is in
