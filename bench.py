@@ -293,8 +293,8 @@ def run_density(args, mb, torch, dev, rank, world, local_rank, dist_on, barrier)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dist", default=DEFAULT_DIST)
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
