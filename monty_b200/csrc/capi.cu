@@ -93,6 +93,29 @@ int ensure(mb200_rng* rng, void** p, size_t* cap, size_t bytes) {
   return MB200_OK;
 }
 
+// One lgamma-of-integers table per device (samplers.cuh: m_lgamma), built by
+// the device itself the first time a handle or a density call touches it.
+constexpr int kLgammaTableN = 16384;        // == kLgtN
+struct LgammaTable { double* d = nullptr; float* f = nullptr; bool ready = false; };
+LgammaTable g_lgamma_table[64];
+std::mutex g_lgamma_mutex;
+
+cudaError_t ensure_lgamma_table(int device, cudaStream_t st) {
+  if (device < 0 || device >= 64) return cudaSuccess;         // no table: every call computes lgamma
+  std::lock_guard<std::mutex> lock(g_lgamma_mutex);
+  LgammaTable& t = g_lgamma_table[device];
+  if (t.ready) return cudaSuccess;
+  cudaError_t e = cudaMalloc(&t.d, kLgammaTableN * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&t.f, kLgammaTableN * sizeof(float));
+  if (e == cudaSuccess) e = launch_lgamma_table_build(t.d, t.f, kLgammaTableN, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = install_lgamma_table_group_b(t.d, t.f);
+  if (e == cudaSuccess) e = install_lgamma_table_group_c(t.d, t.f);
+  if (e == cudaSuccess) e = install_lgamma_table_density(t.d, t.f);
+  t.ready = e == cudaSuccess;
+  return e;
+}
+
 int reset_err(mb200_rng* rng) {
   CU(cudaMemsetAsync(rng->d_err, 0xFF, sizeof(ErrRec), rng->stream));
   return MB200_OK;
@@ -244,6 +267,7 @@ int mb200_rng_create(uint64_t seed, const uint8_t* seed_state_host, size_t seed_
   CU(cudaGetDeviceProperties(&prop, device));
   rng->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&rng->stream, cudaStreamNonBlocking));
+  CU(ensure_lgamma_table(device, rng->stream));
   CU(cudaMalloc(&rng->d_state, n_streams * 32));
   CU(cudaMalloc(&rng->d_err, sizeof(ErrRec)));
   CU(cudaMallocHost(&rng->h_err, sizeof(ErrRec)));
@@ -620,6 +644,7 @@ int mb200_density_dev(int dens, int real_type, size_t n,
   }
   CU(cudaSetDevice(device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CU(ensure_lgamma_table(device, st));
   if (n == 0) {
     if (sum_dev) CU(cudaMemsetAsync(sum_dev, 0, sizeof(double), st));
     return MB200_OK;
@@ -664,6 +689,7 @@ int mb200_density(int dens, int real_type, size_t n,
     return fail(MB200_ERR_CUDA, nullptr, "no usable CUDA device %d (monty_b200 has no CPU fallback)", device);
   }
   CU(cudaSetDevice(device));
+  CU(ensure_lgamma_table(device, nullptr));
   if (n == 0) { if (sum_out) *sum_out = 0.0; return MB200_OK; }
   void* d_x = nullptr;
   void* d_p[MB200_MAX_PARAMS] = {nullptr, nullptr, nullptr, nullptr};

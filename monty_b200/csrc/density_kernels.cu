@@ -128,6 +128,8 @@ cudaError_t launch_density(int dens, int real_type, const DensityArgs& a, int gr
   }
 }
 
+cudaError_t install_lgamma_table_density(const double* d, const float* f) { return lgt_install(d, f); }
+
 cudaError_t launch_reduce_partials(const double* partial, int n, double* sum, cudaStream_t st) {
   reduce_partials_kernel<<<1, 256, 0, st>>>(partial, n, sum);
   return cudaGetLastError();

@@ -205,4 +205,19 @@ cudaError_t launch_xoshiro_run(int gen, uint64_t seed, int n, uint64_t* values_d
   return cudaGetLastError();
 }
 
+// The lgamma-of-small-integers table behind m_lgamma (samplers.cuh): entry i is
+// what lgamma(i) / lgammaf(i) returns on this device, so a table hit is
+// bit-identical to the call it replaces.
+__global__ void lgt_build_kernel(double* __restrict__ d, float* __restrict__ f, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    d[i] = lgamma(static_cast<double>(i));
+    f[i] = lgammaf(static_cast<float>(i));
+  }
+}
+cudaError_t launch_lgamma_table_build(double* d, float* f, int n, cudaStream_t st) {
+  lgt_build_kernel<<<(n + 255) / 256, 256, 0, st>>>(d, f, n);
+  return cudaGetLastError();
+}
+
 }  // namespace mb200

@@ -25,4 +25,5 @@ cudaError_t launch_sample_group_c(int dist, int real_type, int out_f32, bool val
   }
 #undef MB200_CASE
 }
+cudaError_t install_lgamma_table_group_c(const double* d, const float* f) { return lgt_install(d, f); }
 }  // namespace mb200
