@@ -54,6 +54,7 @@ sorted_sample_kernel(const SampleArgs a) {
   __shared__ unsigned s_count[kSortKeys];
   __shared__ unsigned s_offset[kSortKeys];
   __shared__ unsigned short s_order[kSortTile];
+  __shared__ unsigned s_chunk;                       // next 32-stream chunk of the sorted order
 
   const unsigned n = static_cast<unsigned>(a.n_samples);
   const unsigned pitch = n | 1u;
@@ -76,6 +77,7 @@ sorted_sample_kernel(const SampleArgs a) {
     const unsigned long long base = tile * kSortTile;
     const unsigned count = (n_streams - base) < kSortTile ? static_cast<unsigned>(n_streams - base) : kSortTile;
     if (tid < kSortKeys) s_count[tid] = 0;
+    if (tid == 0) s_chunk = 0;
     __syncthreads();
     // 1. parameters -> shared memory, regime key and rank inside the key
     unsigned key[PER], rank[PER];
@@ -114,44 +116,90 @@ sorted_sample_kernel(const SampleArgs a) {
       s_order[s_offset[key[i]] + rank[i]] = static_cast<unsigned short>(tid + i * kSortBlock);
     }
     __syncthreads();
-    // 3. thread t draws for the t-th stream of the sorted order
+    // 3. warps take 32-stream chunks of the sorted order from a shared counter,
+    //    the expensive regimes (high keys, at the end of the order) first: the
+    //    cost of a chunk varies by an order of magnitude between regimes, and
+    //    with a static assignment the cheap warps would wait at the barrier
+    //    below for the expensive ones
+    const unsigned n_chunks = (count + 31) / 32;
 #pragma unroll 1
-    for (int i = 0; i < PER; ++i) {
-      const unsigned slot = tid + i * kSortBlock;
-      if (slot >= count) continue;                 // the non-existent streams sort last
-      const unsigned j = s_order[slot];
+    for (;;) {
+      unsigned chunk = 0;
+      if ((tid & 31) == 0) chunk = atomicAdd(&s_chunk, 1u);
+      chunk = __shfl_sync(0xffffffffu, chunk, 0);
+      if (chunk >= n_chunks) break;
+      const unsigned slot = (n_chunks - 1 - chunk) * 32 + (tid & 31);
+      const bool exists = slot < count;              // the non-existent streams sort last
+      const unsigned j = exists ? s_order[slot] : 0;
       const unsigned long long stream = base + j;
       T par[NP > 0 ? NP : 1];
 #pragma unroll
       for (int k = 0; k < NP; ++k) par[k] = static_cast<T>(par_s[k * kSortTile + j]);
       typename D::Prep prep;
       OutT* row = out_s + j * pitch;
-      const int e = D::prepare(par, prep, ctx);
-      if (e != kOk) {
-        report_error(a.err, stream, e, nullptr);
-        for (unsigned d = 0; d < n; ++d) row[d] = out_nan<OutT>();
-        continue;
+      bool live = exists;
+      if (exists) {
+        const int e = D::prepare(par, prep, ctx);
+        if (e != kOk) {
+          report_error(a.err, stream, e, nullptr);
+          for (unsigned d = 0; d < n; ++d) row[d] = out_nan<OutT>();
+          live = false;
+        }
       }
       Rng rng;
-      rng.s = load_state(a.state, stream);
-      bool live = true;
-#pragma unroll 1
-      for (unsigned d = 0; d < n; ++d) {
-        OutT y = out_nan<OutT>();
-        if (live) {
-          y = static_cast<OutT>(D::draw(rng, prep, ctx));
-          if (D::DYN_ERR && ctx.err) {
-            // a data-dependent failure inside a composition: the stream is
-            // abandoned and the rest of its output is NaN (as in sample_kernel)
-            report_error(a.err, stream, ctx.err, ctx.err_vals);
-            ctx.err = 0;
-            live = false;
-            y = out_nan<OutT>();
+      if (live) rng.s = load_state(a.state, stream);
+      const bool touched = live;
+      if constexpr (D::DEFER) {
+        // Rejection loop with the expensive accept test deferred: a lane whose
+        // candidate fails the cheap squeeze parks it; the parked candidates of
+        // the warp are tested together once half the warp waits (or nobody can
+        // run), so the ~250-instruction test executes with many lanes active
+        // instead of once per warp-iteration for the one or two lanes that
+        // need it.  Per stream nothing changes: same words, same operations.
+        unsigned d = 0;
+        bool parked = false;
+        typename D::Cand cand;
+        for (;;) {
+          const bool run = live && d < n && !parked;
+          const unsigned m_run = __ballot_sync(0xffffffffu, run);
+          unsigned m_park = __ballot_sync(0xffffffffu, parked);
+          if ((m_run | m_park) == 0) break;
+          if (run) {
+            T value;
+            const int st = D::attempt(rng, prep, ctx, cand, value);
+            if (st == 1) row[d++] = static_cast<OutT>(value);
+            else if (st == 2) parked = true;
+          }
+          m_park = __ballot_sync(0xffffffffu, parked);
+          const unsigned m_next = __ballot_sync(0xffffffffu, live && d < n && !parked);
+          if (m_park != 0 && (__popc(m_park) >= 16 || m_next == 0)) {
+            if (parked) {
+              T value;
+              if (D::slow(prep, ctx, cand, value)) row[d++] = static_cast<OutT>(value);
+              parked = false;
+            }
           }
         }
-        row[d] = y;
+      } else {
+#pragma unroll 1
+        for (unsigned d = 0; d < n; ++d) {
+          if (!exists) break;
+          OutT y = out_nan<OutT>();
+          if (live) {
+            y = static_cast<OutT>(D::draw(rng, prep, ctx));
+            if (D::DYN_ERR && ctx.err) {
+              // a data-dependent failure inside a composition: the stream is
+              // abandoned and the rest of its output is NaN (as in sample_kernel)
+              report_error(a.err, stream, ctx.err, ctx.err_vals);
+              ctx.err = 0;
+              live = false;
+              y = out_nan<OutT>();
+            }
+          }
+          row[d] = y;
+        }
       }
-      store_state(a.state, stream, rng.s);
+      if (touched) store_state(a.state, stream, rng.s);
     }
     __syncthreads();
     // 4. the tile's output range is contiguous: coalesced copy out
