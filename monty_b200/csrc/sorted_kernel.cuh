@@ -1,14 +1,14 @@
 // sorted_kernel.cuh -- samplers whose cost depends on the REGIME their
 // per-stream parameters select (binomial: constant / inversion / BTRS;
 // Poisson: Knuth / Hormann / Cauchy; gamma: small / exponential / large;
-// hypergeometric: HIN / H2PE; ...), for short batches (n_samples <= 16: the
+// hypergeometric: HIN / H2PE; ...), for short batches (n_samples <= 64: the
 // dust2 SIR-step shape, BASELINE configs[2] and [3]).
 //
 // In the generic kernel a warp holds 32 consecutive streams, so with
 // per-stream parameters spanning the regimes every warp executes every regime
 // one after the other: ncu shows 4-10 active lanes per instruction
 // (profiles/r01_binomial_d1_ncu_summary.txt, r01_hypergeometric_...).  Here a
-// CTA takes a tile of 512 consecutive streams and
+// CTA takes a tile of 2048 consecutive streams and
 //   1. classifies each stream from its parameters alone (D::regime(), a few
 //      compares -- none of the set-up work),
 //   2. counting-sorts the tile by regime in shared memory (ballot-free:
@@ -18,8 +18,10 @@
 //      regime-pure except at the <= R-1 boundaries of a tile, so prepare() and
 //      draw() run without regime divergence (rejection-loop trip counts still
 //      vary inside a warp),
-//   4. stages the draws in shared memory and writes the tile's contiguous
-//      output range [first_stream * n, (first_stream + 512) * n) coalesced.
+//   4. writes each draw straight to its place out[stream * n + d]: these
+//      kernels are compute-bound by an order of magnitude, and not staging
+//      the output keeps shared memory for a 2048-stream tile (64 chunks of 32
+//      for 8 warps: small tail at the tile barrier, few mixed-regime chunks).
 // Generator states are read and written in place (one 32-byte sector per
 // stream, whichever thread handles it).  Results are bit-identical to the
 // generic kernel's: only the assignment of streams to lanes changes.
@@ -31,16 +33,12 @@
 namespace mb200 {
 
 constexpr int kSortBlock = 256;
-constexpr int kSortTile = 512;            // streams per tile, kSortTile / kSortBlock per thread
-constexpr int kSortMaxSamples = 16;
+constexpr int kSortTile = 2048;           // streams per tile, kSortTile / kSortBlock per thread
+constexpr int kSortMaxSamples = 64;
 constexpr int kSortKeys = 16;             // regime keys 0..14, 15 = stream does not exist
 
-template <typename OutT>
-inline size_t sorted_smem_bytes(int n_params, unsigned n_samples, int tables) {
-  const unsigned pitch = n_samples | 1u;                                // odd: bank spread
-  size_t b = sizeof(OutT) * kSortTile * pitch;
-  b = (b + 15) & ~static_cast<size_t>(15);
-  b += sizeof(double) * kSortTile * (n_params > 0 ? n_params : 1);
+inline size_t sorted_smem_bytes(int n_params, int tables) {
+  size_t b = sizeof(double) * kSortTile * (n_params > 0 ? n_params : 1);
   if (tables != kNoTables) b += sizeof(TableSmem);
   return b;
 }
@@ -57,12 +55,8 @@ sorted_sample_kernel(const SampleArgs a) {
   __shared__ unsigned s_chunk;                       // next 32-stream chunk of the sorted order
 
   const unsigned n = static_cast<unsigned>(a.n_samples);
-  const unsigned pitch = n | 1u;
-  OutT* out_s = reinterpret_cast<OutT*>(smem_raw);
-  size_t off = (sizeof(OutT) * kSortTile * pitch + 15) & ~static_cast<size_t>(15);
-  double* par_s = reinterpret_cast<double*>(smem_raw + off);
-  off += sizeof(double) * kSortTile * (NP > 0 ? NP : 1);
-  TableSmem* ts = reinterpret_cast<TableSmem*>(smem_raw + off);
+  double* par_s = reinterpret_cast<double*>(smem_raw);
+  TableSmem* ts = reinterpret_cast<TableSmem*>(smem_raw + sizeof(double) * kSortTile * (NP > 0 ? NP : 1));
 
   Ctx ctx;
   ctx.err = 0;
@@ -136,7 +130,7 @@ sorted_sample_kernel(const SampleArgs a) {
 #pragma unroll
       for (int k = 0; k < NP; ++k) par[k] = static_cast<T>(par_s[k * kSortTile + j]);
       typename D::Prep prep;
-      OutT* row = out_s + j * pitch;
+      OutT* row = out + stream * n;                  // this stream's draws, written as they come
       bool live = exists;
       if (exists) {
         const int e = D::prepare(par, prep, ctx);
@@ -201,28 +195,13 @@ sorted_sample_kernel(const SampleArgs a) {
       }
       if (touched) store_state(a.state, stream, rng.s);
     }
-    __syncthreads();
-    // 4. the tile's output range is contiguous: coalesced copy out
-    OutT* const dst = out + base * n;
-    const unsigned total = count * n;
-    if (n == 1) {
-      for (unsigned e = tid; e < total; e += kSortBlock) dst[e] = out_s[e * pitch];
-    } else {
-      unsigned r = tid / n, c = tid - r * n;       // element e = r * n + c, advanced by kSortBlock
-      const unsigned dr = kSortBlock / n, dc = kSortBlock - dr * n;
-      for (unsigned e = tid; e < total; e += kSortBlock) {
-        dst[e] = out_s[r * pitch + c];
-        r += dr; c += dc;
-        if (c >= n) { c -= n; ++r; }
-      }
-    }
-    __syncthreads();
+    __syncthreads();                                 // par_s / s_order are reused by the next tile
   }
 }
 
 template <class D, typename T, typename OutT>
 cudaError_t launch_sorted_t(const SampleArgs& a, int sm_count, cudaStream_t st) {
-  const size_t smem = sorted_smem_bytes<OutT>(D::NP, static_cast<unsigned>(a.n_samples), D::TABLES);
+  const size_t smem = sorted_smem_bytes(D::NP, D::TABLES);
   cudaError_t e = cudaFuncSetAttribute(sorted_sample_kernel<D, T, OutT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
@@ -239,7 +218,7 @@ cudaError_t launch_sorted_t(const SampleArgs& a, int sm_count, cudaStream_t st) 
 template <class D>
 inline bool sorted_kernel_applies(const SampleArgs& a) {
   if (D::REGIMES <= 1 || a.n_samples < 1 || a.n_samples > kSortMaxSamples) return false;
-  if (a.n_streams < 4 * kSortTile) return false;
+  if (a.n_streams < 2048) return false;
   bool any_vector = false;
   for (int k = 0; k < D::NP; ++k) any_vector = any_vector || a.pstride[k] != 0;
   return any_vector;
