@@ -97,6 +97,14 @@ int ensure(mb200_rng* rng, void** p, size_t* cap, size_t bytes) {
 // the device itself the first time a handle or a density call touches it.
 constexpr int kLgammaTableN = 16384;        // == kLgtN
 struct LgammaTable { double* d = nullptr; float* f = nullptr; bool ready = false; };
+// Per-device scratch for the per-block partial sums of the fused density
+// reduction: a ring of slots handed out round-robin, so a call never allocates
+// (cudaMallocAsync after a synchronize costs up to milliseconds: the pool gives
+// its memory back) and up to kPartialSlots calls can be in flight per device.
+constexpr int kPartialSlots = 64;
+constexpr int kPartialSlotDoubles = 2048;     // >= density_grid(): 8 blocks per SM
+struct PartialRing { double* base = nullptr; std::atomic<unsigned> next{0}; };
+PartialRing g_partials[64];
 LgammaTable g_lgamma_table[64];
 std::mutex g_lgamma_mutex;
 
@@ -112,6 +120,9 @@ cudaError_t ensure_lgamma_table(int device, cudaStream_t st) {
   if (e == cudaSuccess) e = install_lgamma_table_group_b(t.d, t.f);
   if (e == cudaSuccess) e = install_lgamma_table_group_c(t.d, t.f);
   if (e == cudaSuccess) e = install_lgamma_table_density(t.d, t.f);
+  if (e == cudaSuccess) {
+    e = cudaMalloc(&g_partials[device].base, sizeof(double) * kPartialSlots * kPartialSlotDoubles);
+  }
   t.ready = e == cudaSuccess;
   return e;
 }
@@ -664,8 +675,15 @@ int mb200_density_dev(int dens, int real_type, size_t n,
   a.log = log;
   const int grid = density_grid(n, sm);
   double* partial = nullptr;
+  bool pooled = false;
   if (sum_dev) {
-    CU(cudaMallocAsync(&partial, grid * sizeof(double), st));
+    if (device < 64 && g_partials[device].base && grid <= kPartialSlotDoubles) {
+      const unsigned slot = g_partials[device].next.fetch_add(1, std::memory_order_relaxed) % kPartialSlots;
+      partial = g_partials[device].base + static_cast<size_t>(slot) * kPartialSlotDoubles;
+      pooled = true;
+    } else {
+      CU(cudaMallocAsync(&partial, grid * sizeof(double), st));
+    }
     a.partial = partial;
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -673,7 +691,7 @@ int mb200_density_dev(int dens, int real_type, size_t n,
   if (sum_dev) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CU(launch_reduce_partials(partial, grid, sum_dev, st));
-    CU(cudaFreeAsync(partial, st));
+    if (!pooled) CU(cudaFreeAsync(partial, st));
   }
   return MB200_OK;
 }

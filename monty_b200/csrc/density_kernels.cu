@@ -24,51 +24,90 @@ __device__ __forceinline__ T ld_arg(const void* p, int is_i32, unsigned long lon
                 : static_cast<T>(static_cast<const double*>(p)[i]);
 }
 
+// number of parameters of density DENS (ref: src/density.cpp signatures)
+template <int DENS> struct DensNP {
+  static constexpr int value =
+    (DENS == MB200_DENS_POISSON || DENS == MB200_DENS_EXPONENTIAL_RATE || DENS == MB200_DENS_EXPONENTIAL_MEAN) ? 1 :
+    (DENS == MB200_DENS_BETA_BINOMIAL_PROB || DENS == MB200_DENS_BETA_BINOMIAL_AB || DENS == MB200_DENS_HYPERGEOMETRIC ||
+     DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_PROB) ? 3 :
+    (DENS == MB200_DENS_TRUNCATED_NORMAL) ? 4 : 2;
+};
+
 template <int DENS, typename T>
-__device__ __forceinline__ T density_eval(const DensityArgs& a, unsigned long long i) {
-  const T x = ld_arg<T>(a.x, a.x_is_i32, i);
-  const bool lg = a.log != 0;
-#define P(k) ld_arg<T>(a.par[k], a.par_is_i32[k], i)
+__device__ __forceinline__ T density_compute(T x, const T* p, bool lg) {
   switch (DENS) {
-  case MB200_DENS_BINOMIAL: return dens_binomial<T>(x, P(0), P(1), lg);
-  case MB200_DENS_NORMAL: return dens_normal<T>(x, P(0), P(1), lg);
-  case MB200_DENS_NEGATIVE_BINOMIAL_MU: return dens_negative_binomial_mu<T>(x, P(0), P(1), lg);
-  case MB200_DENS_NEGATIVE_BINOMIAL_PROB: return dens_negative_binomial_prob<T>(x, P(0), P(1), lg);
-  case MB200_DENS_BETA_BINOMIAL_PROB: return dens_beta_binomial_prob<T>(x, P(0), P(1), P(2), lg);
-  case MB200_DENS_BETA_BINOMIAL_AB: return dens_beta_binomial_ab<T>(x, P(0), P(1), P(2), lg);
-  case MB200_DENS_POISSON: return dens_poisson<T>(x, P(0), lg);
-  case MB200_DENS_UNIFORM: return dens_uniform<T>(x, P(0), P(1), lg);
-  case MB200_DENS_EXPONENTIAL_RATE: return dens_exponential_rate<T>(x, P(0), lg);
-  case MB200_DENS_EXPONENTIAL_MEAN: return dens_exponential_mean<T>(x, P(0), lg);
-  case MB200_DENS_GAMMA_RATE: return dens_gamma_rate<T>(x, P(0), P(1), lg);
-  case MB200_DENS_GAMMA_SCALE: return dens_gamma_scale<T>(x, P(0), P(1), lg);
-  case MB200_DENS_BETA: return dens_beta<T>(x, P(0), P(1), lg);
-  case MB200_DENS_HYPERGEOMETRIC: return dens_hypergeometric<T>(x, P(0), P(1), P(2), lg);
-  case MB200_DENS_LOG_NORMAL: return dens_log_normal<T>(x, P(0), P(1), lg);
-  case MB200_DENS_TRUNCATED_NORMAL: return dens_truncated_normal<T>(x, P(0), P(1), P(2), P(3), lg);
-  case MB200_DENS_CAUCHY: return dens_cauchy<T>(x, P(0), P(1), lg);
-  case MB200_DENS_WEIBULL: return dens_weibull<T>(x, P(0), P(1), lg);
+  case MB200_DENS_BINOMIAL: return dens_binomial<T>(x, p[0], p[1], lg);
+  case MB200_DENS_NORMAL: return dens_normal<T>(x, p[0], p[1], lg);
+  case MB200_DENS_NEGATIVE_BINOMIAL_MU: return dens_negative_binomial_mu<T>(x, p[0], p[1], lg);
+  case MB200_DENS_NEGATIVE_BINOMIAL_PROB: return dens_negative_binomial_prob<T>(x, p[0], p[1], lg);
+  case MB200_DENS_BETA_BINOMIAL_PROB: return dens_beta_binomial_prob<T>(x, p[0], p[1], p[2], lg);
+  case MB200_DENS_BETA_BINOMIAL_AB: return dens_beta_binomial_ab<T>(x, p[0], p[1], p[2], lg);
+  case MB200_DENS_POISSON: return dens_poisson<T>(x, p[0], lg);
+  case MB200_DENS_UNIFORM: return dens_uniform<T>(x, p[0], p[1], lg);
+  case MB200_DENS_EXPONENTIAL_RATE: return dens_exponential_rate<T>(x, p[0], lg);
+  case MB200_DENS_EXPONENTIAL_MEAN: return dens_exponential_mean<T>(x, p[0], lg);
+  case MB200_DENS_GAMMA_RATE: return dens_gamma_rate<T>(x, p[0], p[1], lg);
+  case MB200_DENS_GAMMA_SCALE: return dens_gamma_scale<T>(x, p[0], p[1], lg);
+  case MB200_DENS_BETA: return dens_beta<T>(x, p[0], p[1], lg);
+  case MB200_DENS_HYPERGEOMETRIC: return dens_hypergeometric<T>(x, p[0], p[1], p[2], lg);
+  case MB200_DENS_LOG_NORMAL: return dens_log_normal<T>(x, p[0], p[1], lg);
+  case MB200_DENS_TRUNCATED_NORMAL: return dens_truncated_normal<T>(x, p[0], p[1], p[2], p[3], lg);
+  case MB200_DENS_CAUCHY: return dens_cauchy<T>(x, p[0], p[1], lg);
+  case MB200_DENS_WEIBULL: return dens_weibull<T>(x, p[0], p[1], lg);
   case MB200_DENS_ZI_POISSON:
-    return dens_zi_wrap<T>(x, P(0), dens_poisson<T>(x, P(1), true), lg);
+    return dens_zi_wrap<T>(x, p[0], dens_poisson<T>(x, p[1], true), lg);
   case MB200_DENS_ZI_NEGATIVE_BINOMIAL_MU:
-    return dens_zi_wrap<T>(x, P(0), dens_negative_binomial_mu<T>(x, P(1), P(2), true), lg);
+    return dens_zi_wrap<T>(x, p[0], dens_negative_binomial_mu<T>(x, p[1], p[2], true), lg);
   case MB200_DENS_ZI_NEGATIVE_BINOMIAL_PROB:
-    return dens_zi_wrap<T>(x, P(0), dens_negative_binomial_prob<T>(x, P(1), P(2), true), lg);
+    return dens_zi_wrap<T>(x, p[0], dens_negative_binomial_prob<T>(x, p[1], p[2], true), lg);
   default: return 0;
   }
-#undef P
 }
+
+// Four observations per thread per trip, all their loads issued before the
+// first use: the count densities became short once lgamma of integers is a
+// table look-up, and with one element in flight per thread the kernel waited
+// on HBM latency (ncu: long-scoreboard stall 11.9 per issue,
+// profiles/r01_density_poisson_table_ncu_summary.txt).  Element order per
+// thread and the reduction tree are fixed, so the sum stays reproducible.
+// Only for the light densities: the lgamma-heavy ones (non-integer arguments)
+// are FP64-pipe bound and lose occupancy to the extra registers.
+template <int DENS> struct DensUnroll {
+  static constexpr int value =
+    (DENS == MB200_DENS_POISSON || DENS == MB200_DENS_NORMAL || DENS == MB200_DENS_UNIFORM ||
+     DENS == MB200_DENS_EXPONENTIAL_RATE || DENS == MB200_DENS_EXPONENTIAL_MEAN || DENS == MB200_DENS_CAUCHY ||
+     DENS == MB200_DENS_LOG_NORMAL || DENS == MB200_DENS_WEIBULL || DENS == MB200_DENS_ZI_POISSON) ? 4 : 1;
+};
 
 template <int DENS, typename T>
 __global__ void __launch_bounds__(kDensBlock)
 density_kernel(const DensityArgs a) {
+  constexpr int NPD = DensNP<DENS>::value;
+  constexpr int kDensUnroll = DensUnroll<DENS>::value;
   double acc = 0.0;
+  const bool lg = a.log != 0;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kDensBlock;
-  for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * kDensBlock + threadIdx.x;
-       i < a.n; i += stride) {
-    const double v = static_cast<double>(density_eval<DENS, T>(a, i));
-    if (a.out) a.out[i] = v;
-    acc += v;
+  for (unsigned long long i0 = static_cast<unsigned long long>(blockIdx.x) * kDensBlock + threadIdx.x;
+       i0 < a.n; i0 += stride * kDensUnroll) {
+    T x[kDensUnroll], p[kDensUnroll][NPD];
+#pragma unroll
+    for (int u = 0; u < kDensUnroll; ++u) {
+      const unsigned long long i = i0 + u * stride;
+      if (i < a.n) {
+        x[u] = ld_arg<T>(a.x, a.x_is_i32, i);
+#pragma unroll
+        for (int k = 0; k < NPD; ++k) p[u][k] = ld_arg<T>(a.par[k], a.par_is_i32[k], i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kDensUnroll; ++u) {
+      const unsigned long long i = i0 + u * stride;
+      if (i < a.n) {
+        const double v = static_cast<double>(density_compute<DENS, T>(x[u], p[u], lg));
+        if (a.out) a.out[i] = v;
+        acc += v;
+      }
+    }
   }
   if (a.partial) {
     __shared__ double warp_sum[kDensBlock / 32];
