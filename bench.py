@@ -302,7 +302,9 @@ def main():
     ap.add_argument("--draws", type=int, default=1000)
     ap.add_argument("--out-f32", dest="out_f32", action="store_true",
                     help="float32 device output (only with --real f32)")
-    ap.add_argument("--detail", action="store_true", help="also time the other distributions")
+    ap.add_argument("--detail", action="store_true", help="also time the other distributions (default at 1 GPU)")
+    ap.add_argument("--no-detail", dest="no_detail", action="store_true",
+                    help="skip the per-distribution table of the default 1-GPU run")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="sample", choices=["sample", "density"],
@@ -417,7 +419,7 @@ def main():
         del host_out
 
     detail = None
-    if args.detail and rank == 0:
+    if (args.detail or (world == 1 and not args.no_detail)) and rank == 0:
         detail = {}
         for name, s_d in [("real", (S, D)), ("uniform", (S, D)), ("exponential_rate", (S, D)),
                           ("normal_box_muller", (S, D)), ("normal_polar", (S, D)),
@@ -442,7 +444,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = max(1024, S // 64)
+        n_cpu = max(1024, S // 8)       # ~10 core-seconds of CPU work over the three repeats
         kind, threads, times = cpu_reference_run(args.dist, args.real, n_cpu, D, 3, 1)
         tcpu = float(np.mean(times))
         kind1, _, times1 = cpu_reference_run(args.dist, args.real, n_cpu // 8, D, 2, 1, threads=1)
