@@ -41,6 +41,15 @@
 namespace mb200 {
 
 constexpr int kZigMaxWarps = 20;
+// Row pitch of the output tile in elements: 32 slots of the window + pad slots
+// that hold draws banked for the next window (see ziggurat_body).  The pitch is
+// an ODD number of 16-byte units: rows stay 16-byte aligned for the write-out
+// and the scalar tile stores of lanes l and l + 8 are the only ones that share
+// a bank pair.  More pad slots did not pay: 36 doubles (8-way store conflicts)
+// 450 Gdraws/s, 38 doubles (19 warps fit) 460, 34 doubles 465.
+template <typename OutT> struct ZigTile;
+template <> struct ZigTile<double> { static constexpr int PITCH = 34; };
+template <> struct ZigTile<float> { static constexpr int PITCH = 36; };
 constexpr int kZigCopies = 8;                       // replicas of the {x, y} table
 constexpr float kZigBand = 1.0e-4f;                 // |t| below this: decide in double
 constexpr size_t kZigTableBytes = 256 * kZigCopies * sizeof(double2) + 256 * sizeof(float4);
@@ -213,7 +222,7 @@ __device__ __forceinline__ void zig_word(ZigLane<T, OutT>& L, uint32_t zig_saddr
 template <typename T, typename OutT, bool STANDARD>
 __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
   constexpr int VEC = TileCfg<OutT>::VEC;
-  constexpr int PITCH = TileCfg<OutT>::PITCH;
+  constexpr int PITCH = ZigTile<OutT>::PITCH;
   constexpr int LPR = kTile / VEC;         // lanes per row in the write-out
   constexpr int RPI = 32 / LPR;            // rows per store instruction
   constexpr int STEPS = 32 / RPI;
@@ -278,24 +287,40 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
     uint32_t remaining = exists ? n : 0;
     uint32_t e_lo = ((sm + lane) * nm) & 31u;   // m of this lane's row
     uint32_t wpos = 0;                          // window index * 32
+    // Draws of the NEXT window already sitting in this lane's row.  A lane that
+    // completes its window keeps drawing into the kLead pad slots behind it for
+    // as long as the warp runs clean-up iterations for the lanes that parked
+    // candidates, so those iterations do useful work on (nearly) every lane and
+    // a lane that is ahead absorbs its own next wedge events: 3.7 -> 2.1
+    // clean-up iterations per window with the two pad slots of the double tile.
+    // The banked draws are the stream's next draws in order, so nothing changes
+    // per stream; they move to the front of the row after the write-out.
+    constexpr uint32_t kLead = PITCH - kTile;
+    constexpr uint32_t kSz = sizeof(OutT);
+    uint32_t lead = 0;
     for (;;) {
       const uint32_t room = kTile - e_lo;
       const uint32_t cnt = remaining < room ? remaining : room;
       if (__reduce_max_sync(0xffffffffu, cnt) == 0) break;
       remaining -= cnt;
-      L.p = row_saddr + e_lo * static_cast<uint32_t>(sizeof(OutT));
-      const uint32_t p_end = L.p + cnt * static_cast<uint32_t>(sizeof(OutT));
-      const uint32_t n_hot = __reduce_min_sync(0xffffffffu, cnt);
+      const uint32_t extra = remaining < kLead ? remaining : kLead;     // never past the end of the stream's batch
+      L.p = row_saddr + (e_lo + lead) * kSz;
+      const uint32_t p_end = row_saddr + (e_lo + cnt) * kSz;
+      const uint32_t p_cap = p_end + extra * kSz;
+      const uint32_t n_hot = __reduce_min_sync(0xffffffffu, (p_cap - L.p) / kSz);
+      const bool all_full = __reduce_min_sync(0xffffffffu, cnt) == kTile;
       // hot loop: every lane has room for n_hot more outputs and an iteration
       // emits at most one
 #pragma unroll 4
       for (uint32_t i = 0; i < n_hot; ++i) zig_word<T, OutT, STANDARD>(L, zig_saddr, lane_off, wtab_lane_saddr);
-      // lanes that parked candidates (or had more room) finish here
+      // lanes that parked candidates (or had more room) finish here; the others
+      // run ahead into their pad slots meanwhile
       while (__any_sync(0xffffffffu, L.p < p_end)) {
-        if (L.p < p_end) zig_word<T, OutT, STANDARD>(L, zig_saddr, lane_off, wtab_lane_saddr);
+        if (L.p < p_cap) zig_word<T, OutT, STANDARD>(L, zig_saddr, lane_off, wtab_lane_saddr);
       }
+      lead = L.p > p_end ? (L.p - p_end) / kSz : 0;
       __syncwarp();
-      if (vec_ok && n_hot == kTile) {
+      if (vec_ok && all_full) {
         // every row is full: STEPS x (RPI rows x 256 B / 128 B), loads batched before stores
         constexpr int HALF = STEPS / 2;
         char* const wwin = reinterpret_cast<char*>(wbase + wpos);
@@ -318,6 +343,14 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
         }
       }
       __syncwarp();
+      // banked draws (and a candidate parked behind them) move to the front
+      {
+        OutT carry[kLead];
+#pragma unroll
+        for (uint32_t c = 0; c < kLead; ++c) carry[c] = tile[lane * PITCH + kTile + c];
+#pragma unroll
+        for (uint32_t c = 0; c < kLead; ++c) tile[lane * PITCH + c] = carry[c];
+      }
       e_lo = 0;
       wpos += kTile;
     }
@@ -355,7 +388,7 @@ cudaError_t launch_ziggurat_t(const SampleArgs& a, int sm_count, cudaStream_t st
   if (wpb < 1) wpb = 1;
   unsigned long long grid = (n_tiles + wpb - 1) / wpb;
   if (grid > static_cast<unsigned long long>(sm_count)) grid = sm_count;
-  const size_t smem = sizeof(OutT) * wpb * 32 * TileCfg<OutT>::PITCH + kZigTableBytes;
+  const size_t smem = sizeof(OutT) * wpb * 32 * ZigTile<OutT>::PITCH + kZigTableBytes;
   cudaError_t e = cudaFuncSetAttribute(ziggurat_kernel<T, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
