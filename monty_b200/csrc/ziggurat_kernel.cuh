@@ -38,8 +38,13 @@
 
 #include "sample_kernel.cuh"
 
+#ifndef MB200_ZIG_UNROLL
+#define MB200_ZIG_UNROLL 4
+#endif
+
 namespace mb200 {
 
+constexpr int kZigUnroll = MB200_ZIG_UNROLL;     // hot-loop unrolling (experiments: -DMB200_ZIG_UNROLL=n)
 constexpr int kZigMaxWarps = 20;
 // Row pitch of the output tile in elements: 32 slots of the window + pad slots
 // that hold draws banked for the next window (see ziggurat_body).  The pitch is
@@ -311,7 +316,7 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
       const bool all_full = __reduce_min_sync(0xffffffffu, cnt) == kTile;
       // hot loop: every lane has room for n_hot more outputs and an iteration
       // emits at most one
-#pragma unroll 4
+#pragma unroll kZigUnroll
       for (uint32_t i = 0; i < n_hot; ++i) zig_word<T, OutT, STANDARD>(L, zig_saddr, lane_off, wtab_lane_saddr);
       // lanes that parked candidates (or had more room) finish here; the others
       // run ahead into their pad slots meanwhile
