@@ -13,8 +13,8 @@
 // compartments stay in registers across all steps up to the next observation,
 // and the exponential draw and the Poisson log-density are fused into the same
 // kernel -- one state round trip (32 + 32 B) per observation instead of one
-// per draw.  The weight normalisation, prefix sum and gather run as three
-// small kernels (the particle count is the only parallelism there).
+// per draw.  The weight normalisation, prefix sum and gather run as five small
+// grid-wide kernels per observation.
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -24,8 +24,6 @@
 
 namespace {
 namespace mr = monty::random;
-
-constexpr int kScanThreads = 1024;
 
 struct SirPars { double N, beta, gamma, exp_noise; };
 
@@ -53,6 +51,11 @@ __global__ void sir_run_kernel(uint64_t* states, size_t n, double* comp /* [4][n
   comp[i] = S; comp[n + i] = I; comp[2 * n + i] = R; comp[3 * n + i] = cases;
 }
 
+// ---- weights: four small grid-wide kernels per observation -----------------
+constexpr int kWThreads = 256;
+constexpr int kWPer = 8;                          // consecutive particles per thread
+constexpr int kWChunk = kWThreads * kWPer;        // particles per block
+
 __device__ double block_reduce(double v, bool take_max, double* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = 16; d > 0; d >>= 1) {
@@ -75,35 +78,84 @@ __device__ double block_reduce(double v, bool take_max, double* scratch) {
   return r;
 }
 
-// One block.  w = exp(logw - max), ll += log(mean(w)) + max, cum = cumsum(w / sum(w)),
-// u = one uniform from the filter stream.
-__global__ void __launch_bounds__(kScanThreads)
-sir_weights_kernel(const double* logw, size_t n, double* cum, double* ll, uint64_t* filter_state, double* u_out) {
+// 1. per-block maximum of the log weights
+__global__ void __launch_bounds__(kWThreads)
+sir_max_kernel(const double* logw, size_t n, double* part_max) {
   __shared__ double scratch[32];
-  __shared__ double offs[kScanThreads];
-  const size_t per = (n + kScanThreads - 1) / kScanThreads;
-  const size_t lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+  const size_t base = static_cast<size_t>(blockIdx.x) * kWChunk;
   double m = -INFINITY;
-  for (size_t i = lo; i < hi; ++i) m = fmax(m, logw[i]);
+  for (int k = 0; k < kWPer; ++k) {
+    const size_t i = base + k * kWThreads + threadIdx.x;       // coalesced
+    if (i < n) m = fmax(m, logw[i]);
+  }
   m = block_reduce(m, true, scratch);
+  if (threadIdx.x == 0) part_max[blockIdx.x] = m;
+}
+
+// 2. w = exp(logw - max) into `cum` (unnormalised), per-block sums
+__global__ void __launch_bounds__(kWThreads)
+sir_weight_kernel(const double* logw, size_t n, const double* part_max, int n_blocks, double* cum, double* part_sum,
+                  double* max_out) {
+  __shared__ double scratch[32];
+  double m = -INFINITY;
+  for (int b = threadIdx.x; b < n_blocks; b += kWThreads) m = fmax(m, part_max[b]);
+  m = block_reduce(m, true, scratch);
+  const size_t base = static_cast<size_t>(blockIdx.x) * kWChunk;
   double s = 0;
-  for (size_t i = lo; i < hi; ++i) s += exp(logw[i] - m);
-  const double total = block_reduce(s, false, scratch);
-  double c = 0;
-  for (size_t i = lo; i < hi; ++i) c += exp(logw[i] - m) / total;
-  offs[threadIdx.x] = c;
+  for (int k = 0; k < kWPer; ++k) {
+    const size_t i = base + k * kWThreads + threadIdx.x;
+    if (i < n) { const double w = exp(logw[i] - m); cum[i] = w; s += w; }
+  }
+  s = block_reduce(s, false, scratch);
+  if (threadIdx.x == 0) { part_sum[blockIdx.x] = s; if (blockIdx.x == 0) *max_out = m; }
+}
+
+// 3. one block: exclusive scan of the block sums, ll += log(mean(w)) + max, the filter's uniform
+__global__ void __launch_bounds__(1024)
+sir_total_kernel(double* part_sum, int n_blocks, size_t n, const double* max_in, double* scalars, uint64_t* filter_state) {
+  __shared__ double sh[1024];
+  const int per = (n_blocks + 1023) / 1024;
+  const int lo = threadIdx.x * per, hi = min(lo + per, n_blocks);
+  double s = 0;
+  for (int b = lo; b < hi; ++b) s += part_sum[b];
+  sh[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     double run = 0;
-    for (int t = 0; t < kScanThreads; ++t) { const double v = offs[t]; offs[t] = run; run += v; }
-    *ll += log(total / static_cast<double>(n)) + m;
+    for (int t = 0; t < 1024; ++t) { const double v = sh[t]; sh[t] = run; run += v; }
+    scalars[2] = run;                                               // sum of the weights
+    scalars[0] += log(run / static_cast<double>(n)) + *max_in;      // log-likelihood so far
     auto g = mr::load_state(filter_state, 0);
-    *u_out = mr::random_real<double>(g);
+    scalars[1] = mr::random_real<double>(g);
     mr::store_state(filter_state, 0, g);
   }
   __syncthreads();
-  double run = offs[threadIdx.x];
-  for (size_t i = lo; i < hi; ++i) { run += exp(logw[i] - m) / total; cum[i] = run; }
+  double run = sh[threadIdx.x];
+  for (int b = lo; b < hi; ++b) { const double v = part_sum[b]; part_sum[b] = run; run += v; }
+}
+
+// 4. cum = cumsum(w) / sum(w): scan inside the block's chunk + the block's offset
+__global__ void __launch_bounds__(kWThreads)
+sir_cumsum_kernel(double* cum, size_t n, const double* part_off, const double* scalars) {
+  __shared__ double sh[kWThreads];
+  const size_t base = static_cast<size_t>(blockIdx.x) * kWChunk + static_cast<size_t>(threadIdx.x) * kWPer;
+  double w[kWPer];
+  double s = 0;
+  for (int k = 0; k < kWPer; ++k) { w[k] = base + k < n ? cum[base + k] : 0.0; s += w[k]; }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < kWThreads; d <<= 1) {                       // Hillis-Steele inclusive scan
+    const double v = threadIdx.x >= d ? sh[threadIdx.x - d] : 0.0;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  double run = part_off[blockIdx.x] + sh[threadIdx.x] - s;
+  const double total = scalars[2];
+  for (int k = 0; k < kWPer; ++k) {
+    run += w[k];
+    if (base + k < n) cum[base + k] = run / total;
+  }
 }
 
 // k = findInterval(u / n + j / n, cum) (number of entries <= x), then gather
@@ -132,17 +184,19 @@ extern "C" int mb200_example_sir_filter(mb200_rng* system, mb200_rng* filter,
   if (mb200_rng_sync(system) != MB200_OK || mb200_rng_sync(filter) != MB200_OK) return MB200_ERR_CUDA;
   cudaStream_t st = static_cast<cudaStream_t>(mb200_rng_cuda_stream(system));
   const size_t n = mb200_rng_n_streams(system);
-  double *comp = nullptr, *comp2 = nullptr, *logw = nullptr, *cum = nullptr, *scalars = nullptr;
+  double *comp = nullptr, *comp2 = nullptr, *logw = nullptr, *cum = nullptr, *scalars = nullptr, *part = nullptr;
+  const int n_wblocks = static_cast<int>((n + kWChunk - 1) / kWChunk);
   bool ok = cudaMalloc(&comp, 4 * n * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&comp2, 4 * n * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&logw, n * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&cum, n * sizeof(double)) == cudaSuccess &&
-            cudaMalloc(&scalars, 2 * sizeof(double)) == cudaSuccess;
+            cudaMalloc(&part, 2 * static_cast<size_t>(n_wblocks) * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&scalars, 4 * sizeof(double)) == cudaSuccess;
   if (ok) {
     std::vector<double> init(4 * n, 0.0);
     for (size_t i = 0; i < n; ++i) { init[i] = N - I0; init[n + i] = I0; }
     ok = cudaMemcpyAsync(comp, init.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice, st) == cudaSuccess &&
-         cudaMemsetAsync(scalars, 0, 2 * sizeof(double), st) == cudaSuccess &&
+         cudaMemsetAsync(scalars, 0, 4 * sizeof(double), st) == cudaSuccess &&
          cudaStreamSynchronize(st) == cudaSuccess;
   }
   const SirPars q{N, beta, gamma, exp_noise};
@@ -151,7 +205,12 @@ extern "C" int mb200_example_sir_filter(mb200_rng* system, mb200_rng* filter,
   for (size_t d = 0; ok && d < n_data; ++d) {
     sir_run_kernel<<<grid, block, 0, st>>>(mb200_rng_state_dev(system), n, comp, q, time, data_time[d],
                                            data_incidence[d], logw);
-    sir_weights_kernel<<<1, kScanThreads, 0, st>>>(logw, n, cum, scalars, mb200_rng_state_dev(filter), scalars + 1);
+    double* part_max = part;
+    double* part_sum = part + n_wblocks;
+    sir_max_kernel<<<n_wblocks, kWThreads, 0, st>>>(logw, n, part_max);
+    sir_weight_kernel<<<n_wblocks, kWThreads, 0, st>>>(logw, n, part_max, n_wblocks, cum, part_sum, scalars + 3);
+    sir_total_kernel<<<1, 1024, 0, st>>>(part_sum, n_wblocks, n, scalars + 3, scalars, mb200_rng_state_dev(filter));
+    if (resample) sir_cumsum_kernel<<<n_wblocks, kWThreads, 0, st>>>(cum, n, part_sum, scalars);
     if (resample) {
       sir_resample_kernel<<<grid, block, 0, st>>>(cum, n, scalars + 1, comp, comp2);
       double* t = comp; comp = comp2; comp2 = t;
@@ -166,6 +225,6 @@ extern "C" int mb200_example_sir_filter(mb200_rng* system, mb200_rng* filter,
     }
     ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
   }
-  cudaFree(comp); cudaFree(comp2); cudaFree(logw); cudaFree(cum); cudaFree(scalars);
+  cudaFree(comp); cudaFree(comp2); cudaFree(logw); cudaFree(cum); cudaFree(scalars); cudaFree(part);
   return ok ? MB200_OK : MB200_ERR_CUDA;
 }
