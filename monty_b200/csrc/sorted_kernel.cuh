@@ -161,8 +161,18 @@ sorted_sample_kernel(const SampleArgs a) {
           if (run) {
             T value;
             const int st = D::attempt(rng, prep, ctx, cand, value);
-            if (st == 1) row[d++] = static_cast<OutT>(value);
-            else if (st == 2) parked = true;
+            if (D::DYN_ERR && ctx.err) {
+              // a data-dependent failure inside a composition: the stream is
+              // abandoned and the rest of its output is NaN (as in sample_kernel)
+              report_error(a.err, stream, ctx.err, ctx.err_vals);
+              ctx.err = 0;
+              live = false;
+              for (; d < n; ++d) row[d] = out_nan<OutT>();
+            } else if (st == 1) {
+              row[d++] = static_cast<OutT>(value);
+            } else if (st == 2) {
+              parked = true;
+            }
           }
           m_park = __ballot_sync(0xffffffffu, parked);
           const unsigned m_next = __ballot_sync(0xffffffffu, live && d < n && !parked);
