@@ -32,6 +32,9 @@
 
 namespace mb200 {
 
+#ifndef MB200_SORT_MINBLOCKS
+#define MB200_SORT_MINBLOCKS 3   /* 24 warps per SM at 80 registers: these kernels wait on dependent FP64 chains, occupancy beats the few spills (2: binomial x16 30.7, 3: 35.8, 4: 36.2 but Poisson 46.5 -> 40.0 Gdraws/s) */
+#endif
 constexpr int kSortBlock = 256;
 constexpr int kSortTile = 2048;           // streams per tile, kSortTile / kSortBlock per thread
 constexpr int kSortMaxSamples = 64;
@@ -44,7 +47,7 @@ inline size_t sorted_smem_bytes(int n_params, int tables) {
 }
 
 template <class D, typename T, typename OutT>
-__global__ void __launch_bounds__(kSortBlock, 2)
+__global__ void __launch_bounds__(kSortBlock, MB200_SORT_MINBLOCKS)
 sorted_sample_kernel(const SampleArgs a) {
   constexpr int NP = D::NP;
   constexpr int PER = kSortTile / kSortBlock;
