@@ -247,7 +247,48 @@ sample_kernel(const SampleArgs a) {
         if (!__any_sync(0xffffffffu, e_hi > e_lo)) continue;   // nobody has data in this window
         const bool row_full = e_lo == 0 && e_hi == kTile;
         const bool all_full = vec_ok && __all_sync(0xffffffffu, row_full);
-        if (live) {
+        if constexpr (D::DEFER) {
+          // Rejection samplers in resumable pieces (DistBase::DEFER): every lane
+          // fills ITS slots of the window at its own pace -- one attempt per
+          // trip of this loop -- instead of the warp waiting, draw by draw, for
+          // the lane with the most rejections; candidates that need the
+          // expensive accept test are parked and tested together (see
+          // sorted_kernel.cuh, which runs the same loop over sorted streams).
+          int e = e_lo;
+          bool parked = false;
+          typename D::Cand cand;
+          for (;;) {
+            const bool run = live && e < e_hi && !parked;
+            const unsigned m_run = __ballot_sync(0xffffffffu, run);
+            unsigned m_park = __ballot_sync(0xffffffffu, parked);
+            if ((m_run | m_park) == 0) break;
+            if (run) {
+              T value;
+              const int st = D::attempt(rng, prep, ctx, cand, value);
+              if (D::DYN_ERR && ctx.err) {
+                report_error(a.err, stream, ctx.err, ctx.err_vals);
+                ctx.err = 0;
+                live = false;
+              } else if (st == 1) {
+                row[e++] = static_cast<OutT>(value);
+              } else if (st == 2) {
+                parked = true;
+              }
+            }
+            m_park = __ballot_sync(0xffffffffu, parked);
+            const unsigned m_next = __ballot_sync(0xffffffffu, live && e < e_hi && !parked);
+            if (m_park != 0 && (__popc(m_park) >= 16 || m_next == 0)) {
+              if (parked) {
+                T value;
+                if (D::slow(prep, ctx, cand, value)) row[e++] = static_cast<OutT>(value);
+                parked = false;
+              }
+            }
+          }
+          if (!live) {
+            for (; e < e_hi; ++e) row[e] = out_nan<OutT>();
+          }
+        } else if (live) {
           if (all_full && D::UNROLL == 2) {
             // tiny draw(): the whole window straight-line, VEC draws per store
 #pragma unroll
@@ -277,7 +318,7 @@ sample_kernel(const SampleArgs a) {
             live = false;
           }
         }
-        if (!live) {
+        if (!D::DEFER && !live) {
           for (int e = e_lo; e < e_hi; ++e) row[e] = out_nan<OutT>();
         }
         __syncwarp();
