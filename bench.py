@@ -389,7 +389,12 @@ def main():
     # end to end through the host-buffer C-ABI call (what the R glue calls)
     e2e = None
     if rank == 0 or dist_on:
-        host_out = torch.empty((S, D), dtype=torch.float64, pin_memory=True)
+        try:
+            host_out = torch.empty((S, D), dtype=torch.float64, pin_memory=True)
+            pinned = True
+        except RuntimeError:                     # many ranks on one host can exhaust lockable memory
+            host_out = torch.empty((S, D), dtype=torch.float64)
+            pinned = False
         host_np = host_out.numpy()
         import ctypes as C
         arrs = [np.ascontiguousarray(p) for p in params]
@@ -415,7 +420,7 @@ def main():
         e2e = {"value": world * S * D / dt / 1e9, "unit": "Gdraws/s",
                "h2d_bytes_per_step": int(sum(a.nbytes for a in arrs)),
                "d2h_bytes_per_step": int(S * D * 8), "ms_per_step": dt * 1e3,
-               "api": "mb200_rng_sample (host buffers, pinned output)"}
+               "api": "mb200_rng_sample (host buffers, %s output)" % ("pinned" if pinned else "pageable")}
         del host_out
 
     detail = None
