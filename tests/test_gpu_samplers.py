@@ -209,6 +209,39 @@ def test_full_size_config_spot_check(mb, oracle):
     assert abs(m) < 2e-4 and abs(v - 1) < 2e-4
 
 
+@pytest.mark.parametrize("name,draws", [("binomial", 1), ("poisson", 1), ("binomial", 16), ("hypergeometric", 16),
+                                        ("gamma_scale", 16), ("truncated_normal", 16)])
+def test_full_size_sir_step_spot_check(mb, oracle, name, draws):
+    """BASELINE configs C3 / C4 at full size (2^22 streams, per-stream parameters
+    spanning every regime; the regime-sorting kernel), device resident: 4096
+    streams spread over the generator are checked against the reference --
+    integer-valued draws and final states bit for bit."""
+    import torch
+    S = 1 << 22 if draws == 1 else 1 << 20
+    rng = mb.monty_rng_create(S, 42)
+    first = states_of(mb, rng)
+    dev = torch.device("cuda", 0)
+    pars = sampler_cases(S)[name]
+    pd = [torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in pars]
+    out = rng.sample_dev(name, draws, pd)
+    rng.sync()
+    last = states_of(mb, rng)
+    pick = np.linspace(0, S - 1, 4096).astype(np.int64)
+    st = first[pick].copy()
+    exp = oracle.sample(name, st, draws, [p[pick] if p.size == S else p for p in pars])
+    got = out[torch.from_numpy(pick).to(dev)].cpu().numpy()
+    assert np.array_equal(last[pick], st), "final generator states differ"
+    if name in INTEGER_VALUED:
+        assert np.array_equal(got, exp)
+    else:
+        loc = 0.0
+        if name == "truncated_normal":
+            loc = (np.abs(pars[0][pick]) + 6 * np.abs(pars[1][pick]))[:, None] if pars[0].size == S else 6.0
+        scale = np.finfo(np.float64).eps * (np.abs(exp) + loc + 1e-300)
+        assert (np.abs(got - exp) <= 256 * scale).all()
+        assert np.mean(np.abs(got - exp) <= 16 * scale) > 0.999
+
+
 def test_device_resident_matches_host_path(mb):
     import torch
     n, ns = 1000, 50
