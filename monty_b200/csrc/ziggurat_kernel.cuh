@@ -108,6 +108,9 @@ __device__ __noinline__ TailResult<T> ziggurat_tail_from(T u1, X256 state, T x1,
   Rng r{state};
   for (;;) {
     const T u2 = random_real<T>(r);
+    // m_log, not m_log_normal: the result is the same and this routine is cold,
+    // but the shorter variant shifts the register allocation of the whole
+    // kernel and measures 1% slower (453 vs 458 Gdraws/s)
     const T x = m_log(u1) / x1;
     const T y = m_log(u2);
     if (-2 * y > x * x) return TailResult<T>{negative ? x - x1 : x1 - x, r.s};

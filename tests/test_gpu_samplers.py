@@ -184,6 +184,30 @@ def test_scalar_and_vector_parameters_agree(mb):
     assert np.array_equal(mb.monty_random_n_binomial(9, 100.0, 0.3, one), x[:, k])
 
 
+def test_exponential_rate_division_is_ieee(mb):
+    """exponential_rate divides by a per-stream reciprocal refined once per
+    launch (samplers.cuh: ConstDivisor) -- the quotient must be the correctly
+    rounded e / rate for every rate, awkward mantissas and extreme exponents
+    (which take the plain division) included.  exponential_mean(1) returns the
+    same e (e * 1 is exact), so numpy's IEEE division is the checker."""
+    rs = np.random.default_rng(5)
+    n = 4096
+    rate = np.exp(rs.uniform(-40, 40, n))
+    rate[:8] = [1.0, 3.0, 1 / 3, 2.0 ** 52 - 1, np.nextafter(2.0, 1.0), np.nextafter(1.0, 2.0), 0.1, 7.0]
+    rate[8:16] = [1e-300, 1e300, 2.0 ** -901, 2.0 ** 901, 2.0 ** -900, 2.0 ** 900, 5e-324, 1e308]
+    mant = rs.integers(0, 1 << 52, 256, dtype=np.uint64) | np.uint64(0x3FF0000000000000)
+    rate[16:16 + 256] = mant.view(np.float64)
+    rate[272:272 + 64] = np.nextafter(2.0, 1.0) * 2.0 ** rs.integers(-60, 60, 64)
+    a = mb.monty_rng_create(n, 17)
+    b = mb.monty_rng_create(n, 17)
+    e = np.asarray(mb.monty_random_n_exponential_mean(33, 1.0, a))
+    with np.errstate(over="ignore", under="ignore"):
+        expect = e / rate
+    got = np.asarray(mb.monty_random_n_exponential_rate(33, rate, b))
+    assert np.array_equal(got, expect)
+    assert np.array_equal(states_of(mb, a), states_of(mb, b))
+
+
 def test_full_size_config_spot_check(mb, oracle):
     """BASELINE config C2 at full size (2^20 streams x 1000 draws, double,
     ziggurat), device resident: bit-exact on 64 streams spread over the

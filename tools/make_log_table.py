@@ -20,5 +20,13 @@ for i in range(128):
     m = struct.unpack("<Q", struct.pack("<d", float(lc)))[0] & ~((1 << 11) - 1)
     lch = struct.unpack("<d", struct.pack("<Q", m))[0]      # 42 bits: k * Ln2hi + lch is exact
     rows.append((invc, lch, float(lc - mp.mpf(lch))))
+# {1/c, log c high} as 16-byte rows, the low parts as a float array (24 bits of a
+# 2^-44 quantity are plenty): a warp's 32 look-ups touch 16 + 4 cache lines
+print("static __device__ const double2 g_log_tab[128] = {")
 for invc, lch, lcl in rows:
-    print("  {%s, %s, %s, 0.0}," % (invc.hex(), lch.hex(), lcl.hex()))
+    print("  {%s, %s}," % (invc.hex(), lch.hex()))
+print("};")
+print("static __device__ const float g_log_lo[128] = {")
+for i in range(0, 128, 4):
+    print("  " + " ".join("%sf," % float(struct.unpack("<f", struct.pack("<f", r[2]))[0]).hex() for r in rows[i:i + 4]))
+print("};")
