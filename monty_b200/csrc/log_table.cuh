@@ -1,175 +1,49 @@
-// log_table.cuh -- table of the double-precision log used by the samplers
-// (samplers.cuh: m_log).  128 bins over [0.685546875, 1.37109375); bin i holds
-// {1/c_i, log(c_i) high part (42 bits)} in g_log_tab and the low part as a float
-// in g_log_lo; c_i is the bin centre and c_80 == 1 exactly so that arguments next
-// to 1 need no special path.  16-byte rows + a 512-byte array: the 32 look-ups of
-// a warp touch at most 16 + 4 cache lines.
-// Generated with mpmath at 200 bits (the recipe is in tools/make_log_table.py);
+// log_table.cuh -- table and polynomial of the double-precision log used by the
+// samplers (samplers.cuh: fast_log).  32 rows of 16 bytes over [0.6796875,
+// 1.359375): {1/c_i as a float, the low part of log(c_i) as a float, the high
+// part (42 bits)}; c_20 == 1 exactly so that arguments next to 1 need no special
+// path.  The whole table is four cache lines, so the 32 look-ups of a warp cost
+// at most four L1 wavefronts (a 128-row table cost 17 and made the exponential
+// sampler L1-bound).  Generated with mpmath at 300 bits (tools/make_log_table.py);
 // the values are data of this repository, not of the reference.
 #pragma once
 namespace mb200 {
-static __device__ const double2 g_log_tab[128] = {
-  {0x1.745d1745d1746p+0, -0x1.7fafa3bd81000p-2},
-  {0x1.724287f46debcp+0, -0x1.79e26687cf800p-2},
-  {0x1.702e05c0b8170p+0, -0x1.741d876c67800p-2},
-  {0x1.6e1f76b4337c7p+0, -0x1.6e60ee6af1800p-2},
-  {0x1.6c16c16c16c17p+0, -0x1.68ac83e9c6800p-2},
-  {0x1.6a13cd1537290p+0, -0x1.630030b3aa800p-2},
-  {0x1.6816816816817p+0, -0x1.5d5bddf595800p-2},
-  {0x1.661ec6a5122f9p+0, -0x1.57bf753c8d000p-2},
-  {0x1.642c8590b2164p+0, -0x1.522ae0738a000p-2},
-  {0x1.623fa77016240p+0, -0x1.4c9e09e172800p-2},
-  {0x1.6058160581606p+0, -0x1.4718dc271c000p-2},
-  {0x1.5e75bb8d015e7p+0, -0x1.419b423d5e800p-2},
-  {0x1.5c9882b931057p+0, -0x1.3c25277333000p-2},
-  {0x1.5ac056b015ac0p+0, -0x1.36b6776be1000p-2},
-  {0x1.58ed2308158edp+0, -0x1.314f1e1d35800p-2},
-  {0x1.571ed3c506b3ap+0, -0x1.2bef07cdc9000p-2},
-  {0x1.5555555555555p+0, -0x1.269621134d800p-2},
-  {0x1.5390948f40febp+0, -0x1.214456d0eb800p-2},
-  {0x1.51d07eae2f815p+0, -0x1.1bf99635a6800p-2},
-  {0x1.5015015015015p+0, -0x1.16b5ccbacf800p-2},
-  {0x1.4e5e0a72f0539p+0, -0x1.1178e8227e000p-2},
-  {0x1.4cab88725af6ep+0, -0x1.0c42d67616000p-2},
-  {0x1.4afd6a052bf5bp+0, -0x1.07138604d5800p-2},
-  {0x1.49539e3b2d067p+0, -0x1.01eae5626c000p-2},
-  {0x1.47ae147ae147bp+0, -0x1.f991c6cb3b000p-3},
-  {0x1.460cbc7f5cf9ap+0, -0x1.ef5ade4dcf800p-3},
-  {0x1.446f86562d9fbp+0, -0x1.e530effe71000p-3},
-  {0x1.42d6625d51f87p+0, -0x1.db13db0d48800p-3},
-  {0x1.4141414141414p+0, -0x1.d1037f2655800p-3},
-  {0x1.3fb013fb013fbp+0, -0x1.c6ffbc6f00800p-3},
-  {0x1.3e22cbce4a902p+0, -0x1.bd087383bd800p-3},
-  {0x1.3c995a47babe7p+0, -0x1.b31d8575bc800p-3},
-  {0x1.3b13b13b13b14p+0, -0x1.a93ed3c8ad800p-3},
-  {0x1.3991c2c187f63p+0, -0x1.9f6c407089000p-3},
-  {0x1.3813813813814p+0, -0x1.95a5adcf70000p-3},
-  {0x1.3698df3de0748p+0, -0x1.8beafeb38f800p-3},
-  {0x1.3521cfb2b78c1p+0, -0x1.823c16551a000p-3},
-  {0x1.33ae45b57bcb2p+0, -0x1.7898d85444800p-3},
-  {0x1.323e34a2b10bfp+0, -0x1.6f0128b756800p-3},
-  {0x1.30d190130d190p+0, -0x1.6574ebe8c1000p-3},
-  {0x1.2f684bda12f68p+0, -0x1.5bf406b543800p-3},
-  {0x1.2e025c04b8097p+0, -0x1.527e5e4a1b000p-3},
-  {0x1.2c9fb4d812ca0p+0, -0x1.4913d8333b000p-3},
-  {0x1.2b404ad012b40p+0, -0x1.3fb45a5992800p-3},
-  {0x1.29e4129e4129ep+0, -0x1.365fcb0159000p-3},
-  {0x1.288b01288b013p+0, -0x1.2d1610c868000p-3},
-  {0x1.27350b8812735p+0, -0x1.23d712a49c000p-3},
-  {0x1.25e22708092f1p+0, -0x1.1aa2b7e23f000p-3},
-  {0x1.2492492492492p+0, -0x1.1178e8227e000p-3},
-  {0x1.23456789abcdfp+0, -0x1.08598b59e3800p-3},
-  {0x1.21fb78121fb78p+0, -0x1.fe89139dbd000p-4},
-  {0x1.20b470c67c0d9p+0, -0x1.ec739830a1000p-4},
-  {0x1.1f7047dc11f70p+0, -0x1.da72763844000p-4},
-  {0x1.1e2ef3b3fb874p+0, -0x1.c885801bc4800p-4},
-  {0x1.1cf06ada2811dp+0, -0x1.b6ac88dad5800p-4},
-  {0x1.1bb4a4046ed29p+0, -0x1.a4e7640b1b800p-4},
-  {0x1.1a7b9611a7b96p+0, -0x1.9335e5d594800p-4},
-  {0x1.19453808ca29cp+0, -0x1.8197e2f40e000p-4},
-  {0x1.1811811811812p+0, -0x1.700d30aeac000p-4},
-  {0x1.16e0689427379p+0, -0x1.5e95a4d979000p-4},
-  {0x1.15b1e5f75270dp+0, -0x1.4d3115d207800p-4},
-  {0x1.1485f0e0acd3bp+0, -0x1.3bdf5a7d1e800p-4},
-  {0x1.135c81135c811p+0, -0x1.2aa04a4471000p-4},
-  {0x1.12358e75d3033p+0, -0x1.1973bd1465000p-4},
-  {0x1.1111111111111p+0, -0x1.08598b59e3800p-4},
-  {0x1.0fef010fef011p+0, -0x1.eea31c006b800p-5},
-  {0x1.0ecf56be69c90p+0, -0x1.ccb73cdddb000p-5},
-  {0x1.0db20a88f4696p+0, -0x1.aaef2d0fb1000p-5},
-  {0x1.0c9714fbcda3bp+0, -0x1.894aa149fb000p-5},
-  {0x1.0b7e6ec259dc8p+0, -0x1.67c94f2d4b800p-5},
-  {0x1.0a6810a6810a7p+0, -0x1.466aed42de000p-5},
-  {0x1.0953f39010954p+0, -0x1.252f32f8d1800p-5},
-  {0x1.0842108421084p+0, -0x1.0415d89e74000p-5},
-  {0x1.073260a47f7c6p+0, -0x1.c63d2ec14a800p-6},
-  {0x1.0624dd2f1a9fcp+0, -0x1.8492528c8c800p-6},
-  {0x1.05197f7d73404p+0, -0x1.432a925980800p-6},
-  {0x1.0410410410410p+0, -0x1.0205658935800p-6},
-  {0x1.03091b51f5e1ap+0, -0x1.82448a388a000p-7},
-  {0x1.0204081020408p+0, -0x1.010157588d800p-7},
-  {0x1.0101010101010p+0, -0x1.0080559588800p-8},
-  {0x1.0000000000000p+0, 0x0.0p+0},
-  {0x1.fc07f01fc07f0p-1, 0x1.fe02a6b106000p-8},
-  {0x1.f81f81f81f820p-1, 0x1.fc0a8b0fc0000p-7},
-  {0x1.f44659e4a4271p-1, 0x1.7b91b07d5b000p-6},
-  {0x1.f07c1f07c1f08p-1, 0x1.f829b0e783000p-6},
-  {0x1.ecc07b301ecc0p-1, 0x1.39e87b9feb800p-5},
-  {0x1.e9131abf0b767p-1, 0x1.77458f632d800p-5},
-  {0x1.e573ac901e574p-1, 0x1.b42dd71197000p-5},
-  {0x1.e1e1e1e1e1e1ep-1, 0x1.f0a30c0116000p-5},
-  {0x1.de5d6e3f8868ap-1, 0x1.16536eea37800p-4},
-  {0x1.dae6076b981dbp-1, 0x1.341d7961bd000p-4},
-  {0x1.d77b654b82c34p-1, 0x1.51b073f061800p-4},
-  {0x1.d41d41d41d41dp-1, 0x1.6f0d28ae56800p-4},
-  {0x1.d0cb58f6ec074p-1, 0x1.8c345d6319800p-4},
-  {0x1.cd85689039b0bp-1, 0x1.a926d3a4ad000p-4},
-  {0x1.ca4b3055ee191p-1, 0x1.c5e548f5bc000p-4},
-  {0x1.c71c71c71c71cp-1, 0x1.e27076e2af000p-4},
-  {0x1.c3f8f01c3f8f0p-1, 0x1.fec9131dbe800p-4},
-  {0x1.c0e070381c0e0p-1, 0x1.0d77e7cd08800p-3},
-  {0x1.bdd2b899406f7p-1, 0x1.1b72ad52f6000p-3},
-  {0x1.bacf914c1bad0p-1, 0x1.29552f81ff000p-3},
-  {0x1.b7d6c3dda338bp-1, 0x1.371fc201e8800p-3},
-  {0x1.b4e81b4e81b4fp-1, 0x1.44d2b6ccb7800p-3},
-  {0x1.b2036406c80d9p-1, 0x1.526e5e3a1b000p-3},
-  {0x1.af286bca1af28p-1, 0x1.5ff3070a79000p-3},
-  {0x1.ac5701ac5701bp-1, 0x1.6d60fe719d000p-3},
-  {0x1.a98ef606a63bep-1, 0x1.7ab890210d800p-3},
-  {0x1.a6d01a6d01a6dp-1, 0x1.87fa06520c800p-3},
-  {0x1.a41a41a41a41ap-1, 0x1.9525a9cf45000p-3},
-  {0x1.a16d3f97a4b02p-1, 0x1.a23bc1fe2b000p-3},
-  {0x1.9ec8e951033d9p-1, 0x1.af3c94e80b800p-3},
-  {0x1.9c2d14ee4a102p-1, 0x1.bc286742d8800p-3},
-  {0x1.999999999999ap-1, 0x1.c8ff7c79a9800p-3},
-  {0x1.970e4f80cb872p-1, 0x1.d5c216b4fb800p-3},
-  {0x1.948b0fcd6e9e0p-1, 0x1.e27076e2af000p-3},
-  {0x1.920fb49d0e229p-1, 0x1.ef0adcbdc5800p-3},
-  {0x1.8f9c18f9c18fap-1, 0x1.fb9186d5e3800p-3},
-  {0x1.8d3018d3018d3p-1, 0x1.0402594b4d000p-2},
-  {0x1.8acb90f6bf3aap-1, 0x1.0a324e2739000p-2},
-  {0x1.886e5f0abb04ap-1, 0x1.1058bf9ae4800p-2},
-  {0x1.8618618618618p-1, 0x1.1675cababa000p-2},
-  {0x1.83c977ab2beddp-1, 0x1.1c898c1699800p-2},
-  {0x1.8181818181818p-1, 0x1.22941fbcf7800p-2},
-  {0x1.7f405fd017f40p-1, 0x1.2895a13de8000p-2},
-  {0x1.7d05f417d05f4p-1, 0x1.2e8e2bae11800p-2},
-  {0x1.7ad2208e0ecc3p-1, 0x1.347dd9a987800p-2},
-  {0x1.78a4c8178a4c8p-1, 0x1.3a64c55694000p-2},
-  {0x1.767dce434a9b1p-1, 0x1.404308686a000p-2},
-};
-static __device__ const float g_log_lo[128] = {
-  -0x1.471b7a0000000p-44f, -0x1.9ebfd20000000p-45f, -0x1.d870940000000p-45f, -0x1.72aa580000000p-46f,
-  -0x1.0a65320000000p-45f, -0x1.121ee00000000p-44f, -0x1.cc43ac0000000p-44f, -0x1.fadade0000000p-46f,
-  -0x1.eba7080000000p-45f, -0x1.0f3bb80000000p-44f, -0x1.071d900000000p-44f, -0x1.8c2b6e0000000p-47f,
-  -0x1.83454c0000000p-46f, -0x1.15ecdc0000000p-46f, -0x1.38d22a0000000p-44f, -0x1.aa5ba40000000p-45f,
-  -0x1.c8bc1e0000000p-45f, -0x1.a9d5ec0000000p-47f, -0x1.ca42d60000000p-45f, -0x1.b9aae00000000p-45f,
-  -0x1.1e9b8c0000000p-44f, -0x1.70d4b20000000p-45f, -0x1.8fedb20000000p-48f, -0x1.a44ed00000000p-44f,
-  -0x1.bd1ecc0000000p-46f, -0x1.f94bba0000000p-45f, -0x1.2822760000000p-51f, -0x1.409d420000000p-47f,
-  -0x1.9eb6060000000p-45f, -0x1.dc251a0000000p-45f, -0x1.53ddd40000000p-48f, -0x1.8ebbca0000000p-45f,
-  -0x1.e56f2c0000000p-47f, -0x1.98aad60000000p-45f, -0x1.8262860000000p-47f, -0x1.a3baae0000000p-45f,
-  -0x1.e02dba0000000p-46f, -0x1.1d037c0000000p-45f, -0x1.5c76440000000p-46f, -0x1.9cb8b20000000p-46f,
-  -0x1.6bfee00000000p-45f, -0x1.633c8e0000000p-45f, -0x1.58b7960000000p-45f, -0x1.9313c00000000p-48f,
-  -0x1.46fa820000000p-51f, -0x1.3d0ecc0000000p-47f, -0x1.00aa380000000p-46f, -0x1.ca56e40000000p-45f,
-  -0x1.1e778c0000000p-45f, -0x1.0340520000000p-46f, -0x1.5925360000000p-46f, -0x1.267ba80000000p-48f,
-  -0x1.a794020000000p-46f, -0x1.8fd4720000000p-47f, -0x1.8e5ffa0000000p-47f, -0x1.0de64a0000000p-46f,
-  -0x1.87ae1e0000000p-48f, -0x1.f7edd00000000p-47f, -0x1.d068da0000000p-49f, -0x1.ccace20000000p-48f,
-  -0x1.ab076a0000000p-46f, -0x1.9787d40000000p-46f, -0x1.e85aea0000000p-46f, -0x1.5828560000000p-46f,
-  -0x1.02c4520000000p-47f, -0x1.ef41b00000000p-51f, -0x1.67c36e0000000p-48f, -0x1.085a360000000p-49f,
-  -0x1.a55a8c0000000p-48f, -0x1.b2a0820000000p-48f, -0x1.fc66460000000p-48f, -0x1.006b800000000p-51f,
-  -0x1.101c060000000p-47f, -0x1.6b86400000000p-49f, -0x1.6245ce0000000p-49f, -0x1.2ee7320000000p-48f,
-  -0x1.ba4f920000000p-53f, -0x1.41904c0000000p-50f, -0x1.9a4a340000000p-49f, -0x1.92bf2c0000000p-51f,
-  0x0.0p+0f, 0x1.e63f0e0000000p-50f, 0x1.e1e7d00000000p-50f, 0x1.25e9280000000p-50f,
-  0x1.7c267c0000000p-49f, 0x1.59ea400000000p-47f, 0x1.3fc18e0000000p-47f, 0x1.b9428e0000000p-49f,
-  0x1.5430be0000000p-48f, 0x1.71a4320000000p-47f, 0x1.cfb29a0000000p-48f, 0x1.dd493c0000000p-51f,
-  0x1.a6edf20000000p-47f, 0x1.915ad60000000p-47f, 0x1.5871420000000p-46f, 0x1.d0c9760000000p-46f,
-  0x1.74f4f60000000p-47f, 0x1.5dd5180000000p-47f, 0x1.96d9a60000000p-45f, 0x1.e860420000000p-45f,
-  0x1.4853020000000p-45f, 0x1.dd40f40000000p-45f, 0x1.4705f40000000p-45f, 0x1.0deaba0000000p-45f,
-  0x1.eae43a0000000p-46f, 0x1.0dbaaa0000000p-46f, 0x1.06bbe40000000p-47f, 0x1.1098200000000p-47f,
-  0x1.ad6d900000000p-45f, 0x1.58524e0000000p-45f, 0x1.fcda340000000p-45f, 0x1.350e7e0000000p-45f,
-  0x1.0fd6120000000p-46f, 0x1.c9e5c80000000p-46f, 0x1.73f4f60000000p-46f, 0x1.357a180000000p-47f,
-  0x1.8a53560000000p-45f, 0x1.037b8a0000000p-48f, 0x1.c4dee80000000p-47f, 0x1.6a00500000000p-45f,
-  0x1.83c0e80000000p-44f, 0x1.fb67c60000000p-46f, 0x1.65e2420000000p-46f, 0x1.a917ae0000000p-44f,
-  0x1.4c370c0000000p-44f, 0x1.556e920000000p-44f, 0x1.7a81cc0000000p-44f, 0x1.f8f0440000000p-44f,
+// offset 0x3fe5c00000000000; P(r) = -1/2 + r c1 + ... + r^7 c7
+constexpr unsigned long long kLogOff = 0x3fe5c00000000000ull;
+static __constant__ double c_log_poly[7] = {0x1.5555555555555p-2, -0x1.0000000001b30p-2, 0x1.999999999cb08p-3, -0x1.5555544ad6d35p-3, 0x1.249248324d77ap-3, -0x1.001a1f3c514b0p-3, 0x1.c74bf070fdf8dp-4};
+struct __align__(16) LogRow { float invc, lo; double hi; };
+static __device__ const LogRow g_log_tab[32] = {
+  {0x1.745d180000000p+0f, -0x1.44fb7a0000000p-44f, -0x1.7fafa5bd81000p-2},
+  {0x1.6c16c20000000p+0f, -0x1.0769320000000p-45f, -0x1.68ac8589c6800p-2},
+  {0x1.642c860000000p+0f, -0x1.ea57080000000p-45f, -0x1.522ae1b38a000p-2},
+  {0x1.5c98820000000p+0f, -0x1.7aad4c0000000p-46f, -0x1.3c25255333000p-2},
+  {0x1.5555560000000p+0f, -0x1.c53c1e0000000p-45f, -0x1.269623134d800p-2},
+  {0x1.4e5e0a0000000p+0f, -0x1.1e058c0000000p-44f, -0x1.1178e6c27e000p-2},
+  {0x1.47ae140000000p+0f, -0x1.b83ecc0000000p-46f, -0x1.f991c3cb3b000p-3},
+  {0x1.4141420000000p+0f, -0x1.9932060000000p-45f, -0x1.d10383e655800p-3},
+  {0x1.3b13b20000000p+0f, -0x1.ca6f2c0000000p-47f, -0x1.a93ed8c8ad800p-3},
+  {0x1.3521d00000000p+0f, -0x1.deddba0000000p-46f, -0x1.823c18551a000p-3},
+  {0x1.2f684c0000000p+0f, -0x1.6c3ee00000000p-45f, -0x1.5bf407b543800p-3},
+  {0x1.29e4120000000p+0f, -0x1.07ea080000000p-53f, -0x1.365fc6c159000p-3},
+  {0x1.24924a0000000p+0f, -0x1.15f78c0000000p-45f, -0x1.1178ee227e000p-3},
+  {0x1.1f70480000000p+0f, -0x1.a814020000000p-46f, -0x1.da72783844000p-4},
+  {0x1.1a7b960000000p+0f, -0x1.882e1e0000000p-48f, -0x1.9335e4d594800p-4},
+  {0x1.15b1e60000000p+0f, -0x1.ab0f6a0000000p-46f, -0x1.4d31165207800p-4},
+  {0x1.1111120000000p+0f, -0x1.a488a40000000p-48f, -0x1.08599959e3800p-4},
+  {0x1.0c97140000000p+0f, -0x1.311a8c0000000p-48f, -0x1.894a8349fb000p-5},
+  {0x1.0842100000000p+0f, -0x1.011c060000000p-47f, -0x1.0415c89e74000p-5},
+  {0x1.0410420000000p+0f, -0x1.99b27c0000000p-48f, -0x1.0205a38935000p-6},
+  {0x1.0000000000000p+0f, 0x0.0p+0f, 0x0.0p+0},
+  {0x1.f07c200000000p-1f, 0x1.c0267c0000000p-49f, 0x1.f82990e783000p-6},
+  {0x1.e1e1e20000000p-1f, 0x1.53b0be0000000p-48f, 0x1.f0a30a0116000p-5},
+  {0x1.d41d420000000p-1f, 0x1.a65df20000000p-47f, 0x1.6f0d272e56800p-4},
+  {0x1.c71c720000000p-1f, 0x1.73f4f60000000p-47f, 0x1.e27074e2af000p-4},
+  {0x1.bacf920000000p-1f, 0x1.4b77020000000p-45f, 0x1.29552c41ff000p-3},
+  {0x1.af286c0000000p-1f, 0x1.ea643a0000000p-46f, 0x1.5ff3060a79000p-3},
+  {0x1.a41a420000000p-1f, 0x1.ade1900000000p-45f, 0x1.9525a80f45000p-3},
+  {0x1.99999a0000000p-1f, 0x1.12d6120000000p-46f, 0x1.c8ff7a79a9800p-3},
+  {0x1.8f9c180000000p-1f, 0x1.90e3560000000p-45f, 0x1.fb918bd5e3800p-3},
+  {0x1.8618620000000p-1f, 0x1.8448e80000000p-44f, 0x1.1675c97aba000p-2},
+  {0x1.7d05f40000000p-1f, 0x1.4c2f0c0000000p-44f, 0x1.2e8e2bee11800p-2},
 };
 }  // namespace mb200
