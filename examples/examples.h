@@ -34,6 +34,12 @@ int mb200_example_sir_filter(mb200_rng* system, mb200_rng* filter,
                              const double* data_time, const double* data_incidence, size_t n_data,
                              int resample, double* log_likelihood, double* final_state_host);
 
+/* Evaluates one of the samplers' own math routines (csrc/samplers.cuh) on n
+ * host doubles, for the accuracy tests: fn 0 = fast_log, 1 = m_log_normal
+ * (positive normal arguments), 2 = cos_0_2pi (0 <= x <= 2 pi), 3 = sqrt_normal
+ * (positive normal arguments), 4 = the toolkit's sqrt. */
+int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

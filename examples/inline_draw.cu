@@ -98,3 +98,41 @@ extern "C" int mb200_example_inline_draw(mb200_rng* rng, int dist, int real_type
   if (a.out) cudaFree(a.out);
   return rc;
 }
+
+// ---- probe of the samplers' own math routines ----------------------------------
+namespace {
+__global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* __restrict__ y, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (fn) {
+    case 0: r = mb200::fast_log(v); break;
+    case 1: r = mb200::m_log_normal(v); break;
+    case 2: r = mb200::cos_0_2pi(v); break;
+    case 3: r = mb200::sqrt_normal(v); break;
+    case 4: r = sqrt(v); break;
+    default: r = 0.0; break;
+  }
+  y[i] = r;
+}
+}  // namespace
+
+extern "C" int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n) {
+  if (!x_host || !y_host || fn < 0 || fn > 4) return MB200_ERR_ARG;
+  double *dx = nullptr, *dy = nullptr;
+  int rc = MB200_OK;
+  if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&dy, n * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(dx, x_host, n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    rc = MB200_ERR_CUDA;
+  }
+  if (rc == MB200_OK) {
+    math_probe_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(fn, dx, dy, n);
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpy(y_host, dy, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      rc = MB200_ERR_CUDA;
+    }
+  }
+  if (dx) cudaFree(dx);
+  if (dy) cudaFree(dy);
+  return rc;
+}

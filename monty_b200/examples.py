@@ -15,6 +15,18 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 lib.mb200_example_inline_draw.restype = C.c_int
 lib.mb200_example_sir_filter.restype = C.c_int
+lib.mb200_example_math_probe.restype = C.c_int
+
+MATH_FN = {"fast_log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4}
+
+
+def math_probe(fn, x):
+    """The samplers' own math routines (csrc/samplers.cuh) evaluated on the device."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    check(lib.mb200_example_math_probe(C.c_int(MATH_FN[fn]), x.ctypes.data_as(C.c_void_p),
+                                       y.ctypes.data_as(C.c_void_p), C.c_size_t(x.size)))
+    return y
 
 
 def inline_draw(state, dist, params=()):
