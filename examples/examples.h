@@ -34,6 +34,17 @@ int mb200_example_sir_filter(mb200_rng* system, mb200_rng* filter,
                              const double* data_time, const double* data_incidence, size_t n_data,
                              int resample, double* log_likelihood, double* final_state_host);
 
+/* One multinomial draw per stream through monty::random::multinomial<real_type>
+ * (state, size, prob, prob_len, ret) inside a kernel: the same draws as
+ * mb200_rng_multinomial(..., n_samples = 1, ...).  size_host: 1 or n_streams
+ * values; prob_host: prob_len (<= 16) values per column, prob_cols = 1 or
+ * n_streams columns; out_host: n_streams x prob_len doubles, stream-major.
+ * Invalid input gives a row of NaN (the reference's fatal error). */
+int mb200_example_inline_multinomial(mb200_rng* rng, int real_type,
+                                     const double* size_host, size_t size_len,
+                                     const double* prob_host, int prob_len, size_t prob_cols,
+                                     double* out_host);
+
 /* Evaluates one of the samplers' own math routines (csrc/samplers.cuh) on n
  * host doubles, for the accuracy tests: fn 0 = fast_log, 1 = m_log_normal
  * (positive normal arguments), 2 = cos_0_2pi (0 <= x <= 2 pi), 3 = sqrt_normal

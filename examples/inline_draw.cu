@@ -99,6 +99,64 @@ extern "C" int mb200_example_inline_draw(mb200_rng* rng, int dist, int real_type
   return rc;
 }
 
+// ---- monty::random::multinomial inside a kernel ----------------------------------
+namespace {
+template <typename T>
+__global__ void inline_multinomial_kernel(uint64_t* states, size_t n, const double* __restrict__ size, unsigned size_stride,
+                                          const double* __restrict__ prob, int prob_len, unsigned prob_stride,
+                                          double* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  auto g = monty::random::load_state(states, i);
+  T pr[16], ret[16];
+  for (int k = 0; k < prob_len; ++k) pr[k] = static_cast<T>(prob[static_cast<size_t>(prob_stride) * i * prob_len + k]);
+  monty::random::multinomial<T>(g, static_cast<T>(size[size_stride ? i : 0]), pr, prob_len, ret);
+  for (int k = 0; k < prob_len; ++k) out[i * prob_len + k] = static_cast<double>(ret[k]);
+  monty::random::store_state(states, i, g);
+}
+}  // namespace
+
+extern "C" int mb200_example_inline_multinomial(mb200_rng* rng, int real_type,
+                                                const double* size_host, size_t size_len,
+                                                const double* prob_host, int prob_len, size_t prob_cols,
+                                                double* out_host) {
+  if (!rng || !size_host || !prob_host || !out_host || prob_len < 1 || prob_len > 16) return MB200_ERR_ARG;
+  if (cudaSetDevice(mb200_rng_device(rng)) != cudaSuccess) return MB200_ERR_CUDA;
+  if (mb200_rng_sync(rng) != MB200_OK) return MB200_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(mb200_rng_cuda_stream(rng));
+  const size_t n = mb200_rng_n_streams(rng);
+  if ((size_len != 1 && size_len != n) || (prob_cols != 1 && prob_cols != n)) return MB200_ERR_ARG;
+  double *d_size = nullptr, *d_prob = nullptr, *d_out = nullptr;
+  int rc = MB200_OK;
+  if (cudaMalloc(&d_size, size_len * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&d_prob, prob_cols * prob_len * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&d_out, n * prob_len * sizeof(double)) != cudaSuccess ||
+      cudaMemcpyAsync(d_size, size_host, size_len * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(d_prob, prob_host, prob_cols * prob_len * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    rc = MB200_ERR_CUDA;
+  }
+  if (rc == MB200_OK) {
+    const unsigned block = 128, grid = static_cast<unsigned>((n + block - 1) / block);
+    uint64_t* states = mb200_rng_state_dev(rng);
+    if (real_type == MB200_REAL_F32) {
+      inline_multinomial_kernel<float><<<grid, block, 0, st>>>(states, n, d_size, size_len == 1 ? 0u : 1u, d_prob, prob_len,
+                                                               prob_cols == 1 ? 0u : 1u, d_out);
+    } else {
+      inline_multinomial_kernel<double><<<grid, block, 0, st>>>(states, n, d_size, size_len == 1 ? 0u : 1u, d_prob, prob_len,
+                                                                prob_cols == 1 ? 0u : 1u, d_out);
+    }
+    if (cudaGetLastError() != cudaSuccess ||
+        cudaMemcpyAsync(out_host, d_out, n * prob_len * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = MB200_ERR_CUDA;
+    }
+  }
+  if (d_size) cudaFree(d_size);
+  if (d_prob) cudaFree(d_prob);
+  if (d_out) cudaFree(d_out);
+  return rc;
+}
+
 // ---- probe of the samplers' own math routines ----------------------------------
 namespace {
 __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* __restrict__ y, size_t n) {

@@ -204,6 +204,44 @@ MONTY_B200_SAMPLER(zi_negative_binomial_mu, D2(DistZiNegativeBinomial, true), 3,
 #undef D1
 #undef D2
 
+// hdr/multinomial.hpp:53-82: chained conditional binomials; `prob` need not be
+// normalised; `ret` receives prob_len counts.  On invalid input (a negative
+// probability, no positive one, or an inner binomial the reference would
+// reject) every entry of `ret` is NaN and the state is left where the failure
+// happened, unless MONTY_B200_TRAP_ON_ERROR turns it into the reference's
+// fatal error.
+template <typename real_type, typename rng_state_type, typename T, typename U>
+__device__ inline void multinomial(rng_state_type& g, real_type size, const T& prob, int prob_len, U ret) {
+  real_type p_tot = 0;
+  bool ok = true;
+  for (int i = 0; i < prob_len; ++i) {
+    if (prob[i] < 0) ok = false;
+    p_tot += prob[i];
+  }
+  if (!ok || p_tot == 0) {
+    detail::fail("multinomial");
+    for (int i = 0; i < prob_len; ++i) ret[i] = detail::nan_value<real_type>();
+    return;
+  }
+  for (int i = 0; i < prob_len - 1; ++i) {
+    if (prob[i] > 0) {
+      const real_type q = static_cast<real_type>(prob[i]) / p_tot;
+      const real_type pi = q < static_cast<real_type>(1) ? q : static_cast<real_type>(1);
+      const real_type draw = binomial<real_type>(g, size, pi);
+      if (draw != draw) {
+        for (int k = 0; k < prob_len; ++k) ret[k] = detail::nan_value<real_type>();
+        return;
+      }
+      ret[i] = draw;
+      size -= draw;
+      p_tot -= prob[i];
+    } else {
+      ret[i] = 0;
+    }
+  }
+  ret[prob_len - 1] = size;
+}
+
 // hdr/normal.hpp:23-93: the algorithm is a template parameter, box_muller the
 // default (which gamma and truncated_normal use implicitly)
 template <typename real_type, algorithm::normal A = algorithm::normal::box_muller, typename rng_state_type>

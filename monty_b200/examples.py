@@ -17,6 +17,26 @@ lib.mb200_example_inline_draw.restype = C.c_int
 lib.mb200_example_sir_filter.restype = C.c_int
 lib.mb200_example_math_probe.restype = C.c_int
 
+lib.mb200_example_inline_multinomial.restype = C.c_int
+
+
+def inline_multinomial(state, size, prob):
+    """One multinomial draw per stream through monty::random::multinomial() inside
+    a kernel.  prob: (prob_len,) shared or (n_streams, prob_len); returns
+    (n_streams, prob_len)."""
+    size = np.ascontiguousarray(np.atleast_1d(np.asarray(size, dtype=np.float64)))
+    prob = np.ascontiguousarray(np.asarray(prob, dtype=np.float64))
+    cols = 1 if prob.ndim == 1 else prob.shape[0]
+    prob_len = prob.shape[-1]
+    out = np.empty((state.n_streams, prob_len), dtype=np.float64)
+    check(lib.mb200_example_inline_multinomial(
+        state.handle, C.c_int(1 if state.real_type == "f32" else 0),
+        size.ctypes.data_as(C.c_void_p), C.c_size_t(size.size),
+        prob.ctypes.data_as(C.c_void_p), C.c_int(prob_len), C.c_size_t(cols),
+        out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 MATH_FN = {"fast_log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4}
 
 

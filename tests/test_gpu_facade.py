@@ -45,6 +45,36 @@ def test_inline_draw_equals_bulk_path(mb, ex, name, rt):
     assert np.array_equal(states_of(mb, a), states_of(mb, b))
 
 
+def test_inline_multinomial_equals_bulk_path(mb, ex):
+    """monty::random::multinomial (hdr/multinomial.hpp:53-82) called inside a
+    kernel: the counts and the states of mb200_rng_multinomial (which
+    test_gpu_samplers.py pins to the reference), shared and per-stream
+    probabilities, zero probabilities included; rows sum to size."""
+    n = 2000
+    rs = np.random.RandomState(4)
+    shared = np.array([0.1, 0.0, 0.4, 0.5, 0.2, 0.0, 1.3])
+    per_stream = np.abs(rs.randn(n, 6)) * (rs.rand(n, 6) > 0.2)
+    per_stream[:, 3] += 0.01
+    size = np.floor(rs.rand(n) * 400)
+    for prob, sz in [(shared, 100.0), (per_stream, size), (shared, size)]:
+        a = mb.monty_rng_create(n, 77)
+        b = mb.monty_rng_create(n, 77)
+        for _ in range(2):
+            inline = ex.inline_multinomial(a, sz, prob)
+            bulk = np.asarray(mb.monty_random_multinomial(sz, prob.T if prob.ndim == 2 else prob, b))
+            assert np.array_equal(inline, bulk.T)
+            assert np.array_equal(inline.sum(axis=1), np.broadcast_to(sz, (n,)))
+        assert np.array_equal(states_of(mb, a), states_of(mb, b))
+    # invalid probabilities: a row of NaN instead of the reference's fatal error
+    bad = np.tile(np.array([0.5, 0.25, 0.25]), (n, 1))
+    bad[7] = [0.5, -0.1, 0.6]
+    bad[9] = 0.0
+    c = mb.monty_rng_create(n, 78)
+    y = ex.inline_multinomial(c, 10.0, bad)
+    assert np.isnan(y[7]).all() and np.isnan(y[9]).all()
+    assert not np.isnan(np.delete(y, [7, 9], axis=0)).any()
+
+
 SIR = dict(N=1000.0, I0=10.0, beta=0.2, gamma=0.1, exp_noise=1e6)
 TIMES = np.arange(4.0, 81.0, 4.0)
 INCIDENCE = np.array([1, 3, 5, 7, 11, 14, 19, 22, 25, 24, 21, 18, 14, 10, 8, 5, 4, 2, 1, 1], dtype=np.float64)
