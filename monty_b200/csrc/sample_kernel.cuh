@@ -163,7 +163,7 @@ __device__ __forceinline__ void write_window_edge(const OutT* tile, OutT* out, c
 
 // T: real_type of the computation; OutT: element type of `out`.
 template <class D, typename T, typename OutT>
-__global__ void __launch_bounds__(kBlock, 5)
+__global__ void __launch_bounds__(kBlock, D::MINBLOCKS)
 sample_kernel(const SampleArgs a) {
   constexpr int VEC = TileCfg<OutT>::VEC;
   constexpr int PITCH = TileCfg<OutT>::PITCH;
