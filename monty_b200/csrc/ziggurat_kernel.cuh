@@ -48,12 +48,14 @@ constexpr int kZigUnroll = MB200_ZIG_UNROLL;     // hot-loop unrolling (experime
 constexpr int kZigMaxWarps = 20;
 // Row pitch of the output tile in elements: 32 slots of the window + pad slots
 // that hold draws banked for the next window (see ziggurat_body).  The pitch is
-// an ODD number of 16-byte units: rows stay 16-byte aligned for the write-out
-// and the scalar tile stores of lanes l and l + 8 are the only ones that share
-// a bank pair.  More pad slots did not pay: 36 doubles (8-way store conflicts)
-// 450 Gdraws/s, 38 doubles (19 warps fit) 460, 34 doubles 465.
+// odd for the double tile: the scalar 64-bit stores of a half-warp then fall in
+// 16 different bank pairs (an even pitch leaves lanes l and l + 8 on the same
+// pair: two wavefronts per half-warp), at the price of odd rows that are only
+// 8-byte aligned (see the write-out).  Measured: 36 doubles (4-way store
+// conflicts) 450 Gdraws/s, 38 doubles (19 warps fit) 460, 34 doubles 457.7, 35 and
+// 37 doubles 465.3 (same box, same day).
 template <typename OutT> struct ZigTile;
-template <> struct ZigTile<double> { static constexpr int PITCH = 34; };
+template <> struct ZigTile<double> { static constexpr int PITCH = 35; };
 template <> struct ZigTile<float> { static constexpr int PITCH = 36; };
 constexpr int kZigCopies = 8;                       // replicas of the {x, y} table
 constexpr float kZigBand = 1.0e-4f;                 // |t| below this: decide in double
@@ -121,6 +123,20 @@ __device__ __noinline__ TailResult<T> ziggurat_tail_from(T u1, X256 state, T x1,
 __device__ __forceinline__ uint32_t bump(uint32_t p, uint32_t by) {
   return __float_as_uint(__fadd_rn(__uint_as_float(p), __uint_as_float(by)));
 }
+
+// elements e and e + 16 of a row (odd rows of the odd-pitch double tile)
+__device__ __forceinline__ double2 zig_lds_pair(uint32_t addr, double) {
+  double2 v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v.x) : "r"(addr));
+  asm volatile("ld.shared.f64 %0, [%1+128];" : "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 zig_lds_pair(uint32_t, float) { return float4{0, 0, 0, 0}; }   // never used
+__device__ __forceinline__ void zig_stg_pair(char* dst, const double2& v) {
+  *reinterpret_cast<double*>(dst) = v.x;
+  *reinterpret_cast<double*>(dst + 128) = v.y;
+}
+__device__ __forceinline__ void zig_stg_pair(char*, const float4&) {}
 
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
@@ -253,10 +269,19 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
   const uint32_t n = static_cast<uint32_t>(a.n_samples);        // host guarantees 2 <= n < 2^25
   const unsigned long long n_warp_tiles = (n_streams + 31) / 32;
   const bool vec_ok = (n % VEC == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  // write-out geometry of this lane: 16-byte unit `sub` of rows rsub + t * RPI
+  // write-out geometry of this lane: 16-byte unit `sub` of rows rsub + t * RPI.
+  // With an odd pitch (SPLIT, the double tile) the odd rows are only 8-byte
+  // aligned: step t then covers rows 4 (t / 2) + (t % 2) + 2 rsub, so that a
+  // step is all-even (one 128-bit access per lane as before) or all-odd (two
+  // 64-bit accesses per lane: elements sub1 and sub1 + 16 of the row, each
+  // half-warp moving 128 contiguous bytes).
+  constexpr bool SPLIT = (PITCH & 1) != 0;
+  static_assert(!SPLIT || (sizeof(OutT) == 8 && RPI == 2), "odd pitch: double tile only");
   const int sub = (lane % LPR) * VEC;
+  const int sub1 = lane % LPR;
   const int rsub = lane / LPR;
-  const uint32_t rd_saddr = tile_saddr + static_cast<uint32_t>((rsub * PITCH + sub) * sizeof(OutT));
+  const uint32_t rd_saddr = tile_saddr + static_cast<uint32_t>(((SPLIT ? 2 * rsub : rsub) * PITCH + sub) * sizeof(OutT));
+  const uint32_t rd1_saddr = tile_saddr + static_cast<uint32_t>((2 * rsub * PITCH + sub1) * sizeof(OutT));
 
   for (;;) {
     // next 32-stream tile (the counter starts at ~0u: reset_err's 0xFF fill)
@@ -274,8 +299,9 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
     uint32_t roff[STEPS];                       // element offset of (row, sub) from wbase, window 0
 #pragma unroll
     for (int t = 0; t < STEPS; ++t) {
-      const uint32_t r = rsub + t * RPI;
-      roff[t] = (r * n - (((sm + r) * nm) & 31u) + sub) * static_cast<uint32_t>(sizeof(OutT));   // bytes
+      const uint32_t r = SPLIT ? 4 * (t >> 1) + (t & 1) + 2 * rsub : rsub + t * RPI;
+      const uint32_t col = (SPLIT && (t & 1)) ? sub1 : sub;
+      roff[t] = (r * n - (((sm + r) * nm) & 31u) + col) * static_cast<uint32_t>(sizeof(OutT));   // bytes
       // opaque: keeps the 16 offsets in registers instead of re-deriving them
       // (6 ALU instructions each) at every window
       asm volatile("" : "+r"(roff[t]));
@@ -337,10 +363,22 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
           V v[HALF];
 #pragma unroll
           for (int t = 0; t < HALF; ++t) {
-            v[t] = lds_vec(rd_saddr + static_cast<uint32_t>((h * HALF + t) * RPI * PITCH * sizeof(OutT)), OutT());
+            const int step = h * HALF + t;
+            if (!SPLIT) {
+              v[t] = lds_vec(rd_saddr + static_cast<uint32_t>(step * RPI * PITCH * sizeof(OutT)), OutT());
+            } else {
+              const uint32_t row0 = static_cast<uint32_t>((4 * (step >> 1) + (step & 1)) * PITCH * sizeof(OutT));
+              if (step & 1) v[t] = zig_lds_pair(rd1_saddr + row0, OutT());
+              else v[t] = lds_vec(rd_saddr + row0, OutT());
+            }
           }
 #pragma unroll
-          for (int t = 0; t < HALF; ++t) *reinterpret_cast<V*>(wwin + roff[h * HALF + t]) = v[t];   // 64-bit base + 32-bit offset
+          for (int t = 0; t < HALF; ++t) {
+            const int step = h * HALF + t;
+            char* const dst = wwin + roff[step];          // 64-bit base + 32-bit offset
+            if (SPLIT && (step & 1)) zig_stg_pair(dst, v[t]);
+            else *reinterpret_cast<V*>(dst) = v[t];
+          }
         }
       } else {
         // ragged window: lane e of step r writes element e of row r if it belongs to the row
