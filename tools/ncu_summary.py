@@ -40,3 +40,19 @@ top = sorted(enumerate(data), key=lambda t: -int(t[1][ix['# Samples']]))[:ntop]
 for n, r in sorted(top):
     st = {k[6:]: int(r[ix[k]]) for k in keys if int(r[ix[k]]) > 0.1 * int(r[ix['# Samples']])}
     print(n, r[ix['Source']].strip()[:58].ljust(58), r[ix['# Samples']].rjust(6), r[ix['Instructions Executed']].rjust(10), st)
+
+# shared-memory / L1 wavefronts per instruction (bank conflicts show up as "excessive")
+wcols = [h for h in hdr if 'avefronts' in h]
+def num(r, h):
+    try: return float(r[ix[h]])
+    except (ValueError, KeyError): return 0.0
+for h in wcols:
+    print("total %-52s %.4g" % (h, sum(num(r, h) for r in data)))
+exc = [h for h in wcols if 'Shared' in h and 'Excessive' in h]
+if exc:
+    h = exc[0]
+    top = [t for t in sorted(enumerate(data), key=lambda t: -num(t[1], h))[:12] if num(t[1], h) > 0]
+    print("instructions with excessive shared-memory wavefronts:", len(top))
+    for n, r in sorted(top):
+        print(n, r[ix['Source']].strip()[:58].ljust(58), "executed", r[ix['Instructions Executed']].rjust(10),
+              " ".join("%s=%.4g" % (c.replace('L1 Wavefronts ', ''), num(r, c)) for c in wcols if 'Shared' in c))
