@@ -61,11 +61,6 @@ constexpr int kZigCopies = 8;                       // replicas of the {x, y} ta
 constexpr float kZigBand = 1.0e-4f;                 // |t| below this: decide in double
 constexpr size_t kZigTableBytes = 256 * kZigCopies * sizeof(double2) + 256 * sizeof(float4);
 
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ void sts_out(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v) : "memory");
 }
