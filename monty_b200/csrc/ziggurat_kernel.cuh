@@ -261,7 +261,7 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
   const uint32_t wtab_lane_saddr = zig_saddr + static_cast<uint32_t>(256 * kZigCopies * sizeof(double2)) - (lane_off >> 3);
   OutT* const out = static_cast<OutT*>(a.out);
   const unsigned long long n_streams = a.n_streams;
-  const uint32_t n = static_cast<uint32_t>(a.n_samples);        // host guarantees 2 <= n < 2^25
+  const uint32_t n = static_cast<uint32_t>(a.n_samples);        // host guarantees 2 <= n <= 2^24
   const unsigned long long n_warp_tiles = (n_streams + 31) / 32;
   const bool vec_ok = (n % VEC == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   // write-out geometry of this lane: 16-byte unit `sub` of rows rsub + t * RPI.
@@ -410,10 +410,11 @@ ziggurat_kernel(const SampleArgs a) {
   else ziggurat_body<T, OutT, false>(a);
 }
 
-// The batched kernel handles 2 <= n_samples < 2^25 (32-bit row offsets) and
-// fewer than 2^36 streams (32-bit tile counter).
+// The batched kernel handles 2 <= n_samples <= 2^24 and fewer than 2^36 streams
+// (32-bit tile counter).  The write-out offsets are 32-bit BYTE offsets from the
+// first row of a warp-tile: (31 n + 62) * 8 must stay below 2^32.
 inline bool ziggurat_kernel_applies(const SampleArgs& a) {
-  return a.n_samples >= 2 && a.n_samples < (1ull << 25) && a.n_streams < (1ull << 36);
+  return a.n_samples >= 2 && a.n_samples <= (1ull << 24) && a.n_streams < (1ull << 36);
 }
 
 template <typename T, typename OutT>

@@ -122,3 +122,28 @@ def test_ziggurat_matches_lockstep_kernel(mb):
     assert np.array_equal(states_of(mb, one), states_of(mb, many))
     d = ulp_distance(np.stack(cols), batch)
     assert (d <= 4).all() and (d > 0).mean() < 2e-3
+
+
+@pytest.mark.parametrize("n_samples", [(1 << 24), (1 << 24) + 2])
+def test_longest_rows(mb, oracle, n_samples):
+    """The batched kernel addresses its write-out with 32-bit byte offsets from
+    the first row of a warp-tile, which bounds it at n_samples <= 2^24; one
+    more and the generic kernel (64-bit addressing) takes over.  34 streams
+    (a full warp-tile and a ragged one) x 1.7e7 draws, device resident: rows
+    0, 30, 31, 32 and 33 against the reference, final states included."""
+    import torch
+    n = 34
+    dev = torch.device("cuda", 0)
+    rng = mb.monty_rng_create(n, 13)
+    first = states_of(mb, rng)
+    p = [torch.zeros(1, dtype=torch.float64, device=dev), torch.ones(1, dtype=torch.float64, device=dev)]
+    out = rng.sample_dev("normal_ziggurat", n_samples, p)
+    rng.sync()
+    last = states_of(mb, rng)
+    pick = np.array([0, 30, 31, 32, 33])
+    st = first[pick].copy()
+    exp = oracle.sample("normal_ziggurat", st, n_samples, [np.array([0.0]), np.array([1.0])])
+    got = out[torch.from_numpy(pick).to(dev)].cpu().numpy()
+    del out
+    assert np.array_equal(last[pick], st)
+    _check(got, exp, [np.array([0.0]), np.array([1.0])], "f64")
