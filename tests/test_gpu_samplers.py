@@ -189,6 +189,20 @@ def test_float_libm_sensitive_samplers_are_bounded(mb, oracle, name, limit):
     assert frac <= limit
 
 
+def test_empty_requests(mb):
+    """n_samples = 0 returns an empty result and leaves every stream alone; a
+    density of no observations is empty (and its device-side sum is 0)."""
+    rng = mb.monty_rng_create(5, 3)
+    before = states_of(mb, rng)
+    y = np.asarray(mb.monty_random_n_real(0, rng))
+    assert y.size == 0
+    z = np.asarray(mb.monty_random_n_binomial(0, 10.0, 0.5, rng))
+    assert z.size == 0
+    assert np.array_equal(states_of(mb, rng), before)
+    d = np.asarray(mb.density.density_poisson(np.zeros(0, dtype=np.int32), np.zeros(0), True))
+    assert d.size == 0
+
+
 def test_scalar_and_vector_parameters_agree(mb):
     """ref: tests/testthat/test-random.R:77-92: a parameter vector behaves like
     independent single-stream generators; a scalar is broadcast."""
