@@ -46,7 +46,7 @@ int mb200_example_inline_multinomial(mb200_rng* rng, int real_type,
                                      double* out_host);
 
 /* Evaluates one of the samplers' own math routines (csrc/samplers.cuh) on n
- * host doubles, for the accuracy tests: fn 0 = fast_log, 1 = m_log_normal
+ * host doubles, for the parity tests: fn 0 = m_log, 1 = m_log_normal
  * (positive normal arguments), 2 = cos_0_2pi (0 <= x <= 2 pi), 3 = sqrt_normal
  * (positive normal arguments), 4 = the toolkit's sqrt. */
 int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n);

@@ -165,7 +165,7 @@ __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* 
   const double v = x[i];
   double r;
   switch (fn) {
-    case 0: r = mb200::fast_log(v); break;
+    case 0: r = mb200::m_log(v); break;
     case 1: r = mb200::m_log_normal(v); break;
     case 2: r = mb200::cos_0_2pi(v); break;
     case 3: r = mb200::sqrt_normal(v); break;

@@ -1,0 +1,280 @@
+// glibc_math.cuh -- double-precision log() and cos() that return glibc 2.39's BITS.
+//
+// The reference's samplers and densities call std::log / std::cos
+// (hdr/normal_box_muller.hpp:27-34, hdr/exponential.hpp:26, hdr/gamma.hpp:36-50,
+// hdr/density.hpp), which on the oracle's host is glibc 2.39's libm.  Those
+// routines are not correctly rounded (log <= 0.52 ulp, cos <= 0.55 ulp), so an
+// accurate device log / cos differs from the reference in the last bit of ~3% of
+// the results -- and Marsaglia-Tsang's (1 + c x)^3 turns a 1-ulp normal into a
+// 16-ulp gamma.  Parity to the north-star's letter needs the same ALGORITHM on
+// the same TABLES, operation for operation:
+//
+//   log : sysdeps/ieee754/dbl-64/e_log.c (Szabolcs Nagy's table-driven log):
+//         128-entry {1/c, log c} table, r = z/c - 1 by one FMA, degree-5
+//         polynomial; a separate degree-11 polynomial with a split r for
+//         x in [1 - 2^-4, 1 + 0x1.09p-4).
+//   cos : sysdeps/ieee754/dbl-64/s_sin.c (IBM Accurate Mathematical Library):
+//         |x| < 0.855 do_cos; < 2.426 do_sin(pi/2 - |x|); < 1.05e8 reduce_sincos
+//         (x - n pi/2 in four pieces) + do_cos / do_sin by quadrant; do_sin /
+//         do_cos = 440-entry {sin, cos}(k/128) double-double table + short
+//         polynomials, TAYLOR_SIN below 0.126.
+//
+// x86-64 glibc selects, by ifunc, the build of these files compiled with
+// -mfma -mavx2 on every CPU that has FMA (all B200 hosts; the build container
+// too), and GCC contracts a*b+c freely in that build.  WHICH products are fused
+// is therefore part of the function's definition; the sequences below follow
+// the instruction stream of that build (__log_fma / __cos_fma of Ubuntu glibc
+// 2.39-0ubuntu8.5), each fused operation written as an explicit FMA.  Tables:
+// glibc_tables.inc (tools/extract_glibc_tables.py).
+//
+// The file also compiles as plain host C++ (g++ -mfma): tests/test_glibc_math.py
+// builds it that way and compares every routine with the live libm on 1e8
+// arguments, so the source that is checked on the CPU is the source that runs on
+// the device (tests/test_gpu_math.py repeats the comparison on the device).
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "glibc_tables.inc"
+
+#if defined(__CUDACC__)
+#define GM_FN __host__ __device__ __forceinline__
+#else
+#define GM_FN static inline
+#endif
+
+namespace mb200 {
+namespace glibc {
+
+struct alignas(16) LogRow { double invc, logc; };
+struct SinCosRow { double sn, ssn, cs, ccs; };
+
+#if defined(__CUDACC__)
+static __device__ const LogRow g_log_tab[128] = GLIBC_LOG_TAB;
+static __device__ __align__(32) const double g_sincos_tab[440] = GLIBC_SINCOS_TAB;
+static __constant__ double c_log_poly[5] = GLIBC_LOG_POLY;
+static __constant__ double c_log_poly1[11] = GLIBC_LOG_POLY1;
+#endif
+#if !defined(__CUDA_ARCH__)
+static const LogRow h_log_tab[128] = GLIBC_LOG_TAB;
+static const double h_sincos_tab[440] = GLIBC_SINCOS_TAB;
+static const double h_log_poly[5] = GLIBC_LOG_POLY;
+static const double h_log_poly1[11] = GLIBC_LOG_POLY1;
+#endif
+
+// ---- primitives: one IEEE operation each, never contracted -------------------
+#if defined(__CUDA_ARCH__)
+GM_FN double f_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+GM_FN double f_add(double a, double b) { return __dadd_rn(a, b); }
+GM_FN double f_sub(double a, double b) { return __dadd_rn(a, -b); }
+GM_FN double f_mul(double a, double b) { return __dmul_rn(a, b); }
+GM_FN uint64_t f_bits(double x) { return static_cast<uint64_t>(__double_as_longlong(x)); }
+GM_FN double f_from_bits(uint64_t u) { return __longlong_as_double(static_cast<long long>(u)); }
+GM_FN double f_i2d(int k) { return __int2double_rn(k); }
+GM_FN LogRow log_row(int i) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(&g_log_tab[i]));
+  return LogRow{v.x, v.y};
+}
+GM_FN SinCosRow sincos_row(int k) {
+  const double2* p = reinterpret_cast<const double2*>(&g_sincos_tab[4 * k]);
+  const double2 a = __ldg(p), b = __ldg(p + 1);
+  return SinCosRow{a.x, a.y, b.x, b.y};
+}
+#define GM_LOG_POLY c_log_poly
+#define GM_LOG_POLY1 c_log_poly1
+#else
+GM_FN double f_fma(double a, double b, double c) { return __builtin_fma(a, b, c); }
+GM_FN double f_add(double a, double b) { volatile double r = a + b; return r; }
+GM_FN double f_sub(double a, double b) { volatile double r = a - b; return r; }
+GM_FN double f_mul(double a, double b) { volatile double r = a * b; return r; }
+GM_FN uint64_t f_bits(double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; }
+GM_FN double f_from_bits(uint64_t u) { double x; std::memcpy(&x, &u, 8); return x; }
+GM_FN double f_i2d(int k) { return static_cast<double>(k); }
+GM_FN LogRow log_row(int i) { return h_log_tab[i]; }
+GM_FN SinCosRow sincos_row(int k) {
+  return SinCosRow{h_sincos_tab[4 * k], h_sincos_tab[4 * k + 1], h_sincos_tab[4 * k + 2], h_sincos_tab[4 * k + 3]};
+}
+#define GM_LOG_POLY h_log_poly
+#define GM_LOG_POLY1 h_log_poly1
+#endif
+GM_FN double f_abs(double x) { return f_from_bits(f_bits(x) & 0x7fffffffffffffffull); }
+GM_FN double f_neg(double x) { return f_from_bits(f_bits(x) ^ 0x8000000000000000ull); }
+
+// ============================================================================
+// log
+// ============================================================================
+constexpr uint64_t kLogOff = 0x3fe6000000000000ull;       // e_log.c: OFF
+constexpr uint64_t kLogNearLo = 0x3fee000000000000ull;    // 1 - 2^-4
+constexpr uint64_t kLogNearSpan = 0x0003090000000000ull;  // (1 + 0x1.09p-4) - (1 - 2^-4), in bits
+
+// x in [1 - 2^-4, 1 + 0x1.09p-4): log1p(r) by a degree-11 polynomial; r^2 / 2 is
+// taken from r split at 2^-27 so that the leading terms are exact.
+GM_FN double log_near_one(double x) {
+  if (f_bits(x) == 0x3ff0000000000000ull) return 0.0;
+  const double* B = GM_LOG_POLY1;
+  const double r = f_sub(x, 1.0);
+  const double r2 = f_mul(r, r);
+  const double r3 = f_mul(r, r2);
+  // y = r3 (B1 + r B2 + r2 B3 + r3 (B4 + r B5 + r2 B6 + r3 (B7 + r B8 + r2 B9 + r3 B10)))
+  const double p12 = f_fma(r, B[2], B[1]);            // B1 + r B2
+  const double p45 = f_fma(r, B[5], B[4]);            // B4 + r B5
+  const double p78 = f_fma(r, B[8], B[7]);            // B7 + r B8
+  const double p123 = f_fma(r2, B[3], p12);
+  const double p456 = f_fma(r2, B[6], p45);
+  double q = f_fma(r2, B[9], p78);                    // B7 + r B8 + r2 B9
+  q = f_fma(r3, B[10], q);
+  q = f_fma(q, r3, p456);
+  q = f_fma(q, r3, p123);                             // y / r3
+  // rhi = r + w - w, w = r 2^27 (both fused with the multiplication)
+  const double c27 = 0x1p27;
+  const double t = f_fma(r, c27, r);                  // r + w
+  const double rhi = f_fma(-c27, r, t);               // (r + w) - w
+  const double rhi2 = f_mul(rhi, rhi);
+  const double rlo = f_sub(r, rhi);
+  const double hi = f_fma(rhi2, B[0], r);             // r + rhi^2 B0
+  double lo = f_sub(r, hi);
+  const double rsum = f_add(r, rhi);
+  lo = f_fma(rhi2, B[0], lo);                         // r - hi + rhi^2 B0
+  const double brlo = f_mul(B[0], rlo);
+  lo = f_fma(brlo, rsum, lo);                         // += B0 rlo (rhi + r)
+  const double y = f_fma(q, r3, lo);                  // y r3-part + lo
+  return f_add(hi, y);
+}
+
+// Positive, finite, normal x outside the window around 1 (the caller checks).
+GM_FN double log_main(uint64_t ix) {
+  const double* A = GM_LOG_POLY;
+  const uint64_t tmp = ix - kLogOff;
+  const int i = static_cast<int>((tmp >> 45) & 127);
+  const int k = static_cast<int>(static_cast<int64_t>(tmp) >> 52);
+  const double z = f_from_bits(ix - (tmp & 0xfff0000000000000ull));
+  const LogRow row = log_row(i);
+  const double kd = f_i2d(k);
+  const double w = f_fma(kd, GLIBC_LOG_LN2HI, row.logc);
+  const double r = f_fma(z, row.invc, -1.0);
+  const double p12 = f_fma(r, A[2], A[1]);
+  const double hi = f_add(r, w);
+  const double r2 = f_mul(r, r);
+  double lo = f_add(f_sub(w, hi), r);
+  lo = f_fma(kd, GLIBC_LOG_LN2LO, lo);
+  const double r3 = f_mul(r, r2);
+  const double p34 = f_fma(r, A[4], A[3]);
+  lo = f_fma(r2, A[0], lo);
+  const double p = f_fma(p34, r2, p12);
+  return f_add(f_fma(r3, p, lo), hi);
+}
+
+// log(x) for every double (special cases as e_log.c, without errno).
+GM_FN double log(double x) {
+  uint64_t ix = f_bits(x);
+  if (ix - kLogNearLo < kLogNearSpan) return log_near_one(x);
+  const uint32_t top = static_cast<uint32_t>(ix >> 48);
+  if (top - 0x0010u >= 0x7ff0u - 0x0010u) {
+    if (ix * 2 == 0) return f_from_bits(0xfff0000000000000ull);                  // log(+-0) = -inf
+    if (ix == 0x7ff0000000000000ull) return x;                                   // log(inf) = inf
+    if ((top & 0x8000u) || (top & 0x7ff0u) == 0x7ff0u) {                         // negative or NaN
+      return (ix & 0x7fffffffffffffffull) > 0x7ff0000000000000ull ? f_add(x, x) : f_from_bits(0x7ff8000000000000ull | 0x8000000000000000ull);
+    }
+    ix = f_bits(f_mul(x, 0x1p52));                                               // subnormal
+    ix -= 52ull << 52;
+  }
+  return log_main(ix);
+}
+
+// log of a positive, finite, normal number (a random_real() output, a ratio of
+// positive normals ...): no special-case test.
+GM_FN double log_positive_normal(double x) {
+  const uint64_t ix = f_bits(x);
+  if (ix - kLogNearLo < kLogNearSpan) return log_near_one(x);
+  return log_main(ix);
+}
+
+// ============================================================================
+// cos
+// ============================================================================
+// TAYLOR_SIN(a*a, a, da), |a| < 0.126
+GM_FN double taylor_sin(double a, double da) {
+  const double xx = f_mul(a, a);
+  double t = f_fma(xx, GLIBC_SC_S5, GLIBC_SC_S4);
+  t = f_fma(xx, t, GLIBC_SC_S3);
+  t = f_fma(xx, t, GLIBC_SC_S2);
+  t = f_fma(xx, t, GLIBC_SC_S1);
+  const double h = f_mul(da, 0.5);
+  t = f_fma(t, a, -h);
+  t = f_fma(xx, t, da);
+  return f_add(a, t);
+}
+
+// do_cos(a, da): cos(a + da), |a| < 0.86
+GM_FN double do_cos(double a, double da) {
+  if (a < 0) da = f_neg(da);
+  const double aa = f_abs(a);
+  const double u = f_add(aa, GLIBC_SC_BIG);
+  const int k = static_cast<int>(static_cast<uint32_t>(f_bits(u)));
+  const double x = f_add(f_sub(aa, f_sub(u, GLIBC_SC_BIG)), da);
+  const double xx = f_mul(x, x);
+  const double ps = f_fma(xx, GLIBC_SC_SN5, GLIBC_SC_SN3);
+  const double s = f_fma(f_mul(x, xx), ps, x);
+  double pc = f_fma(xx, GLIBC_SC_CS6, GLIBC_SC_CS4);
+  pc = f_fma(xx, pc, GLIBC_SC_CS2);
+  const double c = f_mul(xx, pc);
+  const SinCosRow t = sincos_row(k);
+  double cor = f_fma(-s, t.ssn, t.ccs);
+  cor = f_fma(-c, t.cs, cor);
+  cor = f_fma(-s, t.sn, cor);
+  return f_add(t.cs, cor);
+}
+
+// do_sin(a, da): sin(a + da), |a| < 0.86
+GM_FN double do_sin(double a, double da) {
+  const double aa = f_abs(a);
+  if (aa < GLIBC_SC_SIN_TAYLOR_LIMIT) return taylor_sin(a, da);
+  if (a <= 0) da = f_neg(da);
+  const double u = f_add(aa, GLIBC_SC_BIG);
+  const int k = static_cast<int>(static_cast<uint32_t>(f_bits(u)));
+  const double x = f_sub(aa, f_sub(u, GLIBC_SC_BIG));
+  const double xx = f_mul(x, x);
+  const double ps = f_fma(xx, GLIBC_SC_SN5, GLIBC_SC_SN3);
+  const double s = f_add(x, f_fma(f_mul(x, xx), ps, da));
+  double pc = f_fma(xx, GLIBC_SC_CS6, GLIBC_SC_CS4);
+  pc = f_fma(xx, pc, GLIBC_SC_CS2);
+  const double c = f_fma(x, da, f_mul(xx, pc));
+  const SinCosRow t = sincos_row(k);
+  double cor = f_fma(s, t.ccs, t.ssn);
+  cor = f_fma(-c, t.sn, cor);
+  cor = f_fma(s, t.cs, cor);
+  const double res = f_add(t.sn, cor);
+  return f_from_bits((f_bits(res) & 0x7fffffffffffffffull) | (f_bits(a) & 0x8000000000000000ull));
+}
+
+// cos(x) for |x| < 105414350 (s_sin.c: __cos, the branches below 2^26.65); the
+// Box-Muller angle is in (0, 2 pi].  Larger and non-finite arguments are the
+// caller's business (samplers.cuh routes them to the toolkit's cos).
+GM_FN double cos_medium(double x) {
+  const uint32_t k = static_cast<uint32_t>(f_bits(x) >> 32) & 0x7fffffffu;
+  if (k < 0x3e400000u) return 1.0;                       // |x| < 2^-27
+  if (k < 0x3feb6000u) return do_cos(x, 0.0);            // |x| < 0.855469
+  if (k < 0x400368fdu) {                                 // |x| < 2.426265
+    const double y = f_sub(GLIBC_SC_HP0, f_abs(x));
+    const double a = f_add(y, GLIBC_SC_HP1);
+    const double da = f_add(f_sub(y, a), GLIBC_SC_HP1);
+    return do_sin(a, da);
+  }
+  // reduce_sincos: x - n pi/2 as a + da
+  const double t = f_fma(x, GLIBC_SC_HPINV, GLIBC_SC_TOINT);
+  const double xn = f_sub(t, GLIBC_SC_TOINT);
+  const int n = static_cast<int>(static_cast<uint32_t>(f_bits(t))) & 3;
+  double y = f_fma(-xn, GLIBC_SC_MP1, x);
+  y = f_fma(-xn, GLIBC_SC_MP2, y);
+  const double b = f_fma(-xn, GLIBC_SC_PP3, y);
+  double db = f_fma(-xn, GLIBC_SC_PP3, f_sub(y, b));
+  const double a = f_fma(-xn, GLIBC_SC_PP4, b);
+  const double e = f_fma(-xn, GLIBC_SC_PP4, f_sub(b, a));
+  const double da = f_add(db, e);
+  // do_sincos(a, da, n + 1)
+  const double r = (n & 1) ? do_sin(a, da) : do_cos(a, da);
+  return ((n + 1) & 2) ? f_neg(r) : r;
+}
+
+}  // namespace glibc
+}  // namespace mb200

@@ -37,7 +37,7 @@ def inline_multinomial(state, size, prob):
     return out
 
 
-MATH_FN = {"fast_log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4}
+MATH_FN = {"log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4}
 
 
 def math_probe(fn, x):

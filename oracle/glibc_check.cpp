@@ -1,0 +1,82 @@
+// TEST INFRASTRUCTURE ONLY (see oracle/Makefile).
+// Host build of the PRODUCT's glibc-exact log / cos (monty_b200/csrc/glibc_math.cuh
+// compiled as plain C++ with g++ -mfma, every operation explicit) next to the
+// LIVE libm of the host it runs on -- the library the reference's std::log /
+// std::cos resolve to (hdr/normal_box_muller.hpp:27-34).  tests/test_glibc_math.py
+// compares the two on 1e8 arguments per class; tests/test_gpu_math.py uses
+// gm_libm() as the expected value of the device routines.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "../monty_b200/csrc/glibc_math.cuh"
+
+
+static inline uint64_t splitmix(uint64_t& s) {
+  uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+static inline double from_bits(uint64_t u) { double x; std::memcpy(&x, &u, 8); return x; }
+static inline uint64_t bits(double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; }
+
+// kind 0: log of uniform (0, 1] reals as int_to_real makes them
+//      1: log of random positive normal doubles (any exponent)
+//      2: log of values in [0.9, 1.1] (the window around 1 and its edges)
+//      3: cos of 2 pi u, u in (0, 1]  (the Box-Muller angle)
+//      4: cos of values in [-8, 8]
+//      5: log of random bit patterns (special cases: negative, NaN, inf, subnormal)
+// Returns the number of arguments whose result differs in any bit; the first
+// offender is stored in *bad.
+extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
+  int64_t mism = 0;
+  double first = 0;
+#pragma omp parallel for reduction(+ : mism) schedule(static)
+  for (int64_t c = 0; c < (n + 65535) / 65536; ++c) {
+    uint64_t s = seed + 0x1234567ull * static_cast<uint64_t>(c);
+    const int64_t m = (c + 1) * 65536 <= n ? 65536 : n - c * 65536;
+    for (int64_t j = 0; j < m; ++j) {
+      const uint64_t w = splitmix(s);
+      double x, got, want;
+      const double u = static_cast<double>(w >> 11) * 0x1p-53 + 0x1p-54;
+      switch (kind) {
+        case 0: x = u; got = mb200::glibc::log_positive_normal(x); want = std::log(x); break;
+        case 1: x = from_bits((w >> 1) % 0x7fe0000000000000ull + 0x0010000000000000ull);
+                got = mb200::glibc::log_positive_normal(x); want = std::log(x); break;
+        case 2: x = 0.9 + 0.2 * u; got = mb200::glibc::log(x); want = std::log(x); break;
+        case 3: x = 2 * M_PI * u; got = mb200::glibc::cos_medium(x); want = std::cos(x); break;
+        case 4: x = 16 * u - 8; got = mb200::glibc::cos_medium(x); want = std::cos(x); break;
+        default: x = from_bits(w); got = mb200::glibc::log(x); want = std::log(x); break;
+      }
+      const bool same = bits(got) == bits(want) || (got != got && want != want);
+      if (!same) {
+        ++mism;
+#pragma omp critical
+        if (first == 0) first = x;
+      }
+    }
+  }
+  if (bad) *bad = first;
+  return mism;
+}
+extern "C" double gm_log(double x) { return mb200::glibc::log(x); }
+extern "C" double gm_cos(double x) { return mb200::glibc::cos_medium(x); }
+
+// fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt of the live libm, elementwise
+extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    switch (fn) {
+      case 0: y[i] = std::log(x[i]); break;
+      case 1: y[i] = std::cos(x[i]); break;
+      case 2: y[i] = std::exp(x[i]); break;
+      default: y[i] = std::sqrt(x[i]); break;
+    }
+  }
+}
+// the product's routines on the host, elementwise: fn 0 = log, 1 = cos_medium
+extern "C" void gm_port(int fn, const double* x, double* y, int64_t n) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) y[i] = fn == 0 ? mb200::glibc::log(x[i]) : mb200::glibc::cos_medium(x[i]);
+}

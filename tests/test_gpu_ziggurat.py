@@ -6,8 +6,9 @@ precision outside an ambiguity band and in the reference's own double
 expression inside it, and runs the tail out of line -- so the bar is
   * final generator states: bit-exact (every stream consumed exactly the
     reference's number of words);
-  * draws: bit-exact, except tail draws (|z| > x[1] = 3.65..., 3e-4 of draws),
-    which go through log() and may differ by libm ulps (<= 4 ulp asserted).
+  * draws: bit-exact in double, tail draws (|z| > x[1] = 3.65..., 3e-4 of
+    draws) included -- their log() returns glibc's bits (csrc/glibc_math.cuh);
+    float real_type: tail draws go through logf and may differ by its ulps.
 Shapes cover ragged first/last windows (n_samples not a multiple of 32, odd
 n_samples -> scalar store path), n_streams not a multiple of 32, one warp-tile
 problems and enough draws (3.3e7) to hit the tail ~1e4 and the ambiguity band
@@ -42,6 +43,7 @@ def _check(y, exp, pars, rt):
     same = y == exp
     if same.all():
         return 0.0
+    assert rt != "f64", "double draws must be bit-identical: %r vs %r" % (y[~same][:3], exp[~same][:3])
     n = y.shape[0]
     mean = np.broadcast_to(pars[0], (n,))[:, None]
     sd = np.broadcast_to(pars[1], (n,))[:, None]
@@ -121,7 +123,7 @@ def test_ziggurat_matches_lockstep_kernel(mb):
     batch = np.asarray(mb.random._sample(many, "normal_ziggurat", 40, pars)).reshape(40, n)
     assert np.array_equal(states_of(mb, one), states_of(mb, many))
     d = ulp_distance(np.stack(cols), batch)
-    assert (d <= 4).all() and (d > 0).mean() < 2e-3
+    assert (d == 0).all()
 
 
 @pytest.mark.parametrize("n_samples", [(1 << 24), (1 << 24) + 2])

@@ -1,0 +1,166 @@
+#!/usr/bin/env python
+"""Extract the data tables of glibc's double-precision log() and cos().
+
+Why.  The reference's samplers call std::log / std::cos (hdr/normal_box_muller.hpp:
+27-34, hdr/exponential.hpp:26, hdr/gamma.hpp:36-50 ...), i.e. glibc's libm on the
+oracle's host.  glibc's results are NOT correctly rounded (log <= 0.52 ulp, cos
+<= 0.55 ulp), so "the same bits as the reference" means "the same algorithm and
+the same tables as glibc", not "an accurate log".  The algorithms are published
+(log: sysdeps/ieee754/dbl-64/e_log.c, Szabolcs Nagy's table-driven log from ARM
+optimized-routines; cos: sysdeps/ieee754/dbl-64/s_sin.c, the IBM Accurate
+Mathematical Library's do_sin / do_cos over __sincostab) and are restated in
+monty_b200/csrc/glibc_math.cuh (device) and oracle/glibc_math_port.c (CPU check);
+the TABLES are data, read here from the image's own libm.so.6 (glibc 2.39,
+Ubuntu 2.39-0ubuntu8.5, the library the oracle links) and written as hex-float
+literals to
+
+    monty_b200/csrc/glibc_tables.inc
+
+Tables:
+    __log_data      ln2hi, ln2lo, poly[5], poly1[11], tab[128] {invc, logc}
+    __sincostab     440 doubles: {sin hi, sin lo, cos hi, cos lo} of x_k ~ k/128
+    scalar constants of s_sin.c / branred (big, hp0, hp1, mp1, mp2, pp3, pp4,
+    hpinv, toint, sn3, sn5, cs2, cs4, cs6, s1..s5) -- written from their
+    published values and CHECKED to be present in the library's .rodata.
+
+The tables are located by signature (ln2hi followed by ln2lo; {0, 0, 1, 0,
+sin(1/128)}), not by address, so another build of glibc 2.39 works too.
+tests/test_glibc_math.py checks the committed file against mathematical
+properties of the tables and the CPU restatement against the live libm on
+1e7..1e8 arguments.
+"""
+import math
+import os
+import struct
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBM = "/lib/x86_64-linux-gnu/libm.so.6"
+
+LN2HI = float.fromhex("0x1.62e42fefa3800p-1")
+LN2LO = float.fromhex("0x1.ef35793c76730p-45")
+
+# s_sin.c / usncs.h / branred constants (published values)
+SCALARS = {
+    "big": "0x1.8p45", "toint": "0x1.8p52",
+    "hp0": "0x1.921fb54442d18p+0", "hp1": "0x1.1a62633145c07p-54",
+    "hpinv": "0x1.45f306dc9c883p-1",
+    "mp1": "0x1.921fb58000000p+0", "mp2": "-0x1.dde973c000000p-27",
+    "pp3": "-0x1.cb3b398000000p-55", "pp4": "-0x1.d747f23e32ed7p-83",
+    "sn3": "-0x1.5555555555515p-3", "sn5": "0x1.11110e829872fp-7",
+    "cs2": "0x1p-1", "cs4": "-0x1.5555555555535p-5", "cs6": "0x1.6c16bedd9e239p-10",
+    "sin_taylor_limit": "0x1.020c49ba5e354p-3",   # 0.126
+    "s1": "-0x1.5555555555555p-3", "s2": "0x1.1111111110ecep-7", "s3": "-0x1.a01a019db08b8p-13",
+    "s4": "0x1.71de27b9a7ed9p-19", "s5": "-0x1.addffc2fcdf59p-26",
+}
+
+
+def rodata(path):
+    with open(path, "rb") as f:
+        blob = f.read()
+    # ELF64 section headers
+    shoff = struct.unpack_from("<Q", blob, 0x28)[0]
+    shentsize, shnum, shstrndx = struct.unpack_from("<HHH", blob, 0x3A)
+    secs = []
+    for i in range(shnum):
+        name, typ, flags, addr, off, size = struct.unpack_from("<IIQQQQ", blob, shoff + i * shentsize)
+        secs.append((name, addr, off, size))
+    stroff = secs[shstrndx][2]
+    for name, addr, off, size in secs:
+        end = blob.index(b"\0", stroff + name)
+        if blob[stroff + name:end] == b".rodata":
+            return blob, addr, off, size
+    raise SystemExit("no .rodata in " + path)
+
+
+def dbl(blob, off, n):
+    return list(struct.unpack_from("<%dd" % n, blob, off))
+
+
+def find_doubles(blob, off, size, seq):
+    pat = struct.pack("<%dd" % len(seq), *seq)
+    i = blob.find(pat, off, off + size)
+    while i >= 0 and i % 8:
+        i = blob.find(pat, i + 1, off + size)
+    return i
+
+
+def main(out=None):
+    blob, addr, off, size = rodata(LIBM)
+    # ---- __log_data: {ln2hi, ln2lo, poly[5], poly1[11], tab[128]{invc, logc}}
+    # (poly first appears at +0x10; the FMA build has no tab2 in use)
+    i = find_doubles(blob, off, size, [LN2HI, LN2LO])
+    if i < 0:
+        raise SystemExit("log table signature not found")
+    logd = dbl(blob, i, 2 + 5 + 11 + 256)
+    ln2hi, ln2lo = logd[0], logd[1]
+    A = logd[2:7]
+    B = logd[7:18]
+    T = logd[18:18 + 256]
+    assert abs(A[0] + 0.5) < 1e-15 and B[0] == -0.5, (A[0], B[0])
+    # table sanity: invc * c ~ 1 for c in [0.6875 .. 1.375], logc = log(c) to 2^-43
+    for k in range(128):
+        invc, logc = T[2 * k], T[2 * k + 1]
+        assert 0.72 < invc < 1.46, invc
+        assert abs(logc - math.log(1 / invc)) < 2 ** -40, (k, logc)
+    # ---- __sincostab
+    s1 = math.sin(1 / 128)
+    j = off
+    while True:
+        j = find_doubles(blob, j, off + size - j, [0.0, 0.0, 1.0, 0.0])
+        if j < 0:
+            raise SystemExit("sincostab signature not found")
+        if abs(dbl(blob, j + 32, 1)[0] - s1) < 1e-9:
+            break
+        j += 8
+    sct = dbl(blob, j, 440)
+    for k in range(110):
+        sn, ssn, cs, ccs = sct[4 * k:4 * k + 4]
+        assert abs(sn - math.sin(k / 128)) < 1e-8 and abs(cs - math.cos(k / 128)) < 1e-8, k
+        assert abs(ssn) < 2 ** -50 and abs(ccs) < 2 ** -50
+    # ---- scalar constants: confirm each published value occurs in .rodata
+    consts = dict(SCALARS)
+    missing = []
+    for name, hx in consts.items():
+        v = float.fromhex(hx)
+        if find_doubles(blob, off, size, [v]) < 0:
+            missing.append(name)
+    if out is None:
+        return dict(ln2hi=ln2hi, ln2lo=ln2lo, A=A, B=B, T=T, sincos=sct, missing=missing,
+                    log_addr=addr + (i - off), sincos_addr=addr + (j - off))
+    if missing:
+        raise SystemExit("constants not found in libm .rodata: %s" % missing)
+    fh = lambda v: float(v).hex()  # noqa: E731
+    L = []
+    L.append("/* GENERATED by tools/extract_glibc_tables.py -- do not edit.")
+    L.append(" * Numeric data only (hex-float literals, bit-exact): the tables of glibc 2.39's")
+    L.append(" * double-precision log (__log_data) and sin/cos (__sincostab), read from the")
+    L.append(" * image's libm.so.6.  See the tool's docstring for why parity needs them. */")
+    L.append("#define GLIBC_LOG_LN2HI %s" % fh(ln2hi))
+    L.append("#define GLIBC_LOG_LN2LO %s" % fh(ln2lo))
+    L.append("#define GLIBC_LOG_POLY { %s }" % ", ".join(fh(v) for v in A))
+    L.append("#define GLIBC_LOG_POLY1 { %s }" % ", ".join(fh(v) for v in B))
+    L.append("/* tab[128]: {invc, logc} */")
+    L.append("#define GLIBC_LOG_TAB { \\")
+    for k in range(0, 128, 2):
+        L.append("  " + ", ".join("{%s, %s}" % (fh(T[2 * m]), fh(T[2 * m + 1])) for m in (k, k + 1)) + ", \\")
+    L[-1] = L[-1][:-3] + " }"
+    L.append("/* __sincostab[440]: {sin hi, sin lo, cos hi, cos lo} per k = round(128 |x|) */")
+    L.append("#define GLIBC_SINCOS_TAB { \\")
+    for k in range(110):
+        L.append("  " + ", ".join(fh(v) for v in sct[4 * k:4 * k + 4]) + ", \\")
+    L[-1] = L[-1][:-3] + " }"
+    for name, hx in consts.items():
+        L.append("#define GLIBC_SC_%s %s" % (name.upper(), fh(float.fromhex(hx))))
+    with open(out, "w") as f:
+        f.write("\n".join(L) + "\n")
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--probe":
+        r = main(None)
+        print("log_data at 0x%x, sincostab at 0x%x" % (r["log_addr"], r["sincos_addr"]))
+        print("missing scalar constants:", r["missing"])
+    else:
+        main(os.path.join(ROOT, "monty_b200", "csrc", "glibc_tables.inc"))
