@@ -48,16 +48,19 @@ namespace glibc {
 
 struct alignas(16) LogRow { double invc, logc; };
 struct SinCosRow { double sn, ssn, cs, ccs; };
+struct alignas(32) SinCosRow2 { double P, p, Q, q; };    // lock-step rows, see sincos_core
 
 #if defined(__CUDACC__)
 static __device__ const LogRow g_log_tab[128] = GLIBC_LOG_TAB;
 static __device__ __align__(32) const double g_sincos_tab[440] = GLIBC_SINCOS_TAB;
+static __device__ const SinCosRow2 g_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static __constant__ double c_log_poly[5] = GLIBC_LOG_POLY;
 static __constant__ double c_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
 #if !defined(__CUDA_ARCH__)
 static const LogRow h_log_tab[128] = GLIBC_LOG_TAB;
 static const double h_sincos_tab[440] = GLIBC_SINCOS_TAB;
+static const SinCosRow2 h_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static const double h_log_poly[5] = GLIBC_LOG_POLY;
 static const double h_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
@@ -80,6 +83,12 @@ GM_FN SinCosRow sincos_row(int k) {
   const double2 a = __ldg(p), b = __ldg(p + 1);
   return SinCosRow{a.x, a.y, b.x, b.y};
 }
+GM_FN SinCosRow2 sincos_row2(int i) {
+  const double2* p = reinterpret_cast<const double2*>(&g_sincos_rows[i]);
+  const double2 a = __ldg(p), b = __ldg(p + 1);
+  return SinCosRow2{a.x, a.y, b.x, b.y};
+}
+GM_FN double f_sel(bool c, double a, double b) { return c ? a : b; }
 #define GM_LOG_POLY c_log_poly
 #define GM_LOG_POLY1 c_log_poly1
 #else
@@ -94,6 +103,8 @@ GM_FN LogRow log_row(int i) { return h_log_tab[i]; }
 GM_FN SinCosRow sincos_row(int k) {
   return SinCosRow{h_sincos_tab[4 * k], h_sincos_tab[4 * k + 1], h_sincos_tab[4 * k + 2], h_sincos_tab[4 * k + 3]};
 }
+GM_FN SinCosRow2 sincos_row2(int i) { return h_sincos_rows[i]; }
+GM_FN double f_sel(bool c, double a, double b) { return c ? a : b; }
 #define GM_LOG_POLY h_log_poly
 #define GM_LOG_POLY1 h_log_poly1
 #endif
@@ -189,6 +200,41 @@ GM_FN double log_positive_normal(double x) {
   return log_main(ix);
 }
 
+// N logs of positive, finite, normal numbers at once.  The window around 1
+// (1/16 of uniform arguments) costs 27 FP64 operations against the main path's
+// 15, and with 32 independent lanes some lane is in it for 87% of the calls, so
+// in lock-step everyone pays for both, every time.  Here the main path runs for
+// all N arguments and the window's arguments are then worked off in a loop that
+// takes ONE pending argument per lane per trip: the warp makes max-over-lanes
+// trips, 1.5 per 4 uniform arguments instead of 3.5.  Same operations on the
+// same values as N calls of log_positive_normal().
+template <int N>
+GM_FN void log_positive_normal_batch(const double (&x)[N], double (&lg)[N]) {
+  unsigned pend = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < N; ++i) {
+    const uint64_t ix = f_bits(x[i]);
+    if (ix - kLogNearLo < kLogNearSpan) pend |= 1u << i;
+    lg[i] = log_main(ix);
+  }
+  while (pend) {
+    const unsigned low = pend & (0u - pend);
+    double xi = x[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 1; j < N; ++j) xi = (low == (1u << j)) ? x[j] : xi;
+    const double r = log_near_one(xi);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < N; ++j) lg[j] = (low == (1u << j)) ? r : lg[j];
+    pend ^= low;
+  }
+}
+
 // ============================================================================
 // cos
 // ============================================================================
@@ -274,6 +320,76 @@ GM_FN double cos_medium(double x) {
   // do_sincos(a, da, n + 1)
   const double r = (n & 1) ? do_sin(a, da) : do_cos(a, da);
   return ((n + 1) & 2) ? f_neg(r) : r;
+}
+
+// ---- the same function for lock-step execution ---------------------------------
+// cos_medium() branches four ways on the argument and then two or three ways
+// on the quadrant; 32 lanes with independent angles take every path, so a warp
+// pays for all of them in turn (Box-Muller fell from 163 to 64 Gdraws/s).  The
+// formulation below computes the SAME operations on the same values -- every
+// result bit is unchanged, checked against libm like cos_medium -- arranged so
+// that all lanes run one instruction stream:
+//   * both argument reductions are evaluated (3 + 11 operations) and selected;
+//   * do_sin and do_cos share the table look-up, x^2, both polynomials and the
+//     correction chain: with rows stored as {P, p, Q, q} = {sn, ssn, cs, ccs}
+//     for sin and {cs, ccs, -sn, -ssn} for cos, both are
+//         cor = s q + p;  cor = cor - c P;  cor = cor + s Q;  result = P + cor
+//     (negating an operand of an FMA is exact); only s and c differ, and both
+//     variants are computed (4 operations) and selected;
+//   * TAYLOR_SIN (|a| < 0.126, 8% of the angles) stays a branch.
+GM_FN double sincos_core(double a, double da, bool is_sin) {
+  const double aa = f_abs(a);
+  const bool flip = is_sin ? (a <= 0) : (a < 0);
+  const double dx = flip ? f_neg(da) : da;
+  const double u = f_add(aa, GLIBC_SC_BIG);
+  const int k = static_cast<int>(static_cast<uint32_t>(f_bits(u)));
+  const double x0 = f_sub(aa, f_sub(u, GLIBC_SC_BIG));
+  const double x = f_sel(is_sin, x0, f_add(x0, dx));
+  const double xx = f_mul(x, x);
+  const double ps = f_fma(xx, GLIBC_SC_SN5, GLIBC_SC_SN3);
+  const double xxx = f_mul(x, xx);
+  double pc = f_fma(xx, GLIBC_SC_CS6, GLIBC_SC_CS4);
+  pc = f_fma(xx, pc, GLIBC_SC_CS2);
+  const double cc = f_mul(xx, pc);
+  const double s_cos = f_fma(xxx, ps, x);
+  const double s_sin = f_add(x, f_fma(xxx, ps, dx));
+  const double c_sin = f_fma(x, dx, cc);
+  const double s = f_sel(is_sin, s_sin, s_cos);
+  const double c = f_sel(is_sin, c_sin, cc);
+  const SinCosRow2 t = sincos_row2(k + (is_sin ? 110 : 0));
+  double cor = f_fma(s, t.q, t.p);
+  cor = f_fma(-c, t.P, cor);
+  cor = f_fma(s, t.Q, cor);
+  const double res = f_add(t.P, cor);
+  const uint64_t sign = is_sin ? (f_bits(a) & 0x8000000000000000ull) : (f_bits(res) & 0x8000000000000000ull);
+  return f_from_bits((f_bits(res) & 0x7fffffffffffffffull) | sign);
+}
+
+GM_FN double cos_medium_lockstep(double x) {
+  const uint32_t k = static_cast<uint32_t>(f_bits(x) >> 32) & 0x7fffffffu;
+  // |x| >= 2.426265: reduce_sincos
+  const double t = f_fma(x, GLIBC_SC_HPINV, GLIBC_SC_TOINT);
+  const double xn = f_sub(t, GLIBC_SC_TOINT);
+  const int n = static_cast<int>(static_cast<uint32_t>(f_bits(t))) & 3;
+  double y = f_fma(-xn, GLIBC_SC_MP1, x);
+  y = f_fma(-xn, GLIBC_SC_MP2, y);
+  const double b = f_fma(-xn, GLIBC_SC_PP3, y);
+  const double db = f_fma(-xn, GLIBC_SC_PP3, f_sub(y, b));
+  const double a_d = f_fma(-xn, GLIBC_SC_PP4, b);
+  const double da_d = f_add(db, f_fma(-xn, GLIBC_SC_PP4, f_sub(b, a_d)));
+  // 0.855469 <= |x| < 2.426265: sin(pi/2 - |x|)
+  const double yc = f_sub(GLIBC_SC_HP0, f_abs(x));
+  const double a_c = f_add(yc, GLIBC_SC_HP1);
+  const double da_c = f_add(f_sub(yc, a_c), GLIBC_SC_HP1);
+  const bool in_b = k < 0x3feb6000u, in_c = !in_b && k < 0x400368fdu;
+  const double a = in_b ? x : (in_c ? a_c : a_d);
+  const double da = in_b ? 0.0 : (in_c ? da_c : da_d);
+  const bool is_sin = in_c || (!in_b && (n & 1));
+  const bool neg = !in_b && !in_c && ((n + 1) & 2);
+  double r = sincos_core(a, da, is_sin);
+  if (is_sin && f_abs(a) < GLIBC_SC_SIN_TAYLOR_LIMIT) r = taylor_sin(a, da);
+  if (neg) r = f_neg(r);
+  return k < 0x3e400000u ? 1.0 : r;
 }
 
 }  // namespace glibc

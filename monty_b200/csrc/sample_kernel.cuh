@@ -189,6 +189,12 @@ __device__ __forceinline__ void write_window_edge(const OutT* tile, OutT* out, c
   }
 }
 
+// D::draw_batch where the sampler has one (the call must not be instantiated otherwise)
+template <class D, typename T, int N>
+__device__ __forceinline__ void batch_draw(Rng& rng, const typename D::Prep& prep, Ctx& ctx, T (&b)[N]) {
+  if constexpr (D::BATCH > 1) D::draw_batch(rng, prep, ctx, b);
+}
+
 // T: real_type of the computation; OutT: element type of `out`.
 template <class D, typename T, typename OutT>
 __global__ void __launch_bounds__(kBlock, D::MINBLOCKS)
@@ -347,6 +353,21 @@ sample_kernel(const SampleArgs a) {
 #pragma unroll
               for (int e = 0; e < VEC; ++e) v[e] = static_cast<OutT>(D::draw(rng, prep, ctx));
               sts_vec(row_saddr + static_cast<uint32_t>(j * sizeof(OutT)), v);
+            }
+          } else if (all_full && D::UNROLL == 1 && D::BATCH > 1) {
+            // BATCH draws per trip (DistBase::BATCH), then BATCH / VEC vector stores
+            static_assert(D::BATCH == 1 || (D::BATCH % VEC == 0 && kTile % D::BATCH == 0), "batch shape");
+#pragma unroll 1
+            for (int j = 0; j < kTile; j += D::BATCH) {
+              T b[D::BATCH > 1 ? D::BATCH : 1];
+              batch_draw<D, T>(rng, prep, ctx, b);
+#pragma unroll
+              for (int g = 0; g < D::BATCH; g += VEC) {
+                OutT v[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[e] = static_cast<OutT>(b[g + e]);
+                sts_vec(row_saddr + static_cast<uint32_t>((j + g) * sizeof(OutT)), v);
+              }
             }
           } else if (all_full && D::UNROLL == 1) {
 #pragma unroll 1

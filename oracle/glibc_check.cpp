@@ -27,6 +27,8 @@ static inline uint64_t bits(double x) { uint64_t u; std::memcpy(&u, &x, 8); retu
 //      3: cos of 2 pi u, u in (0, 1]  (the Box-Muller angle)
 //      4: cos of values in [-8, 8]
 //      5: log of random bit patterns (special cases: negative, NaN, inf, subnormal)
+//      6, 7, 8: the lock-step formulation of cos on the Box-Muller angle, on
+//         [-1000, 1000], on log-uniform magnitudes below 1.0e8
 // Returns the number of arguments whose result differs in any bit; the first
 // offender is stored in *bad.
 extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
@@ -47,6 +49,10 @@ extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
         case 2: x = 0.9 + 0.2 * u; got = mb200::glibc::log(x); want = std::log(x); break;
         case 3: x = 2 * M_PI * u; got = mb200::glibc::cos_medium(x); want = std::cos(x); break;
         case 4: x = 16 * u - 8; got = mb200::glibc::cos_medium(x); want = std::cos(x); break;
+        case 6: x = 2 * M_PI * u; got = mb200::glibc::cos_medium_lockstep(x); want = std::cos(x); break;
+        case 7: x = 2000 * u - 1000; got = mb200::glibc::cos_medium_lockstep(x); want = std::cos(x); break;
+        case 8: x = from_bits((w >> 1) % 0x4199000000000000ull);        // any magnitude below 1.0e8, log-uniform
+                got = mb200::glibc::cos_medium_lockstep(x); want = std::cos(x); break;
         default: x = from_bits(w); got = mb200::glibc::log(x); want = std::log(x); break;
       }
       const bool same = bits(got) == bits(want) || (got != got && want != want);
@@ -60,8 +66,26 @@ extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
   if (bad) *bad = first;
   return mism;
 }
+// log_positive_normal_batch<4> against four single calls of libm, n groups
+extern "C" int64_t gm_compare_log_batch(uint64_t seed, int64_t n) {
+  int64_t mism = 0;
+#pragma omp parallel for reduction(+ : mism) schedule(static)
+  for (int64_t c = 0; c < n; ++c) {
+    uint64_t s = seed + 0x9e3779b9ull * static_cast<uint64_t>(c);
+    double x[4], lg[4];
+    for (int i = 0; i < 4; ++i) {
+      const uint64_t w = splitmix(s);
+      x[i] = (w & 3) == 0 ? 0.93 + 0.14 * (static_cast<double>(w >> 11) * 0x1p-53)   // many in the window
+                          : static_cast<double>(w >> 11) * 0x1p-53 + 0x1p-54;
+    }
+    mb200::glibc::log_positive_normal_batch<4>(x, lg);
+    for (int i = 0; i < 4; ++i) mism += bits(lg[i]) != bits(std::log(x[i]));
+  }
+  return mism;
+}
 extern "C" double gm_log(double x) { return mb200::glibc::log(x); }
 extern "C" double gm_cos(double x) { return mb200::glibc::cos_medium(x); }
+extern "C" double gm_cos_lockstep(double x) { return mb200::glibc::cos_medium_lockstep(x); }
 
 // fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt of the live libm, elementwise
 extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {

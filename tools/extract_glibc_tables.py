@@ -150,6 +150,17 @@ def main(out=None):
     for k in range(110):
         L.append("  " + ", ".join(fh(v) for v in sct[4 * k:4 * k + 4]) + ", \\")
     L[-1] = L[-1][:-3] + " }"
+    # the same rows arranged for the lock-step formulation of do_sin / do_cos
+    # (glibc_math.cuh: sincos_core): row [kind][k] = {P, p, Q, q} with
+    # sin (kind 1): {sn, ssn, cs, ccs};  cos (kind 0): {cs, ccs, -sn, -ssn}
+    L.append("/* [2][110] rows {P, p, Q, q}: kind 0 (cos) = {cs, ccs, -sn, -ssn}, kind 1 (sin) = {sn, ssn, cs, ccs} */")
+    L.append("#define GLIBC_SINCOS_ROWS { \\")
+    for kind in (0, 1):
+        for k in range(110):
+            sn, ssn, cs, ccs = sct[4 * k:4 * k + 4]
+            row = (sn, ssn, cs, ccs) if kind else (cs, ccs, -sn, -ssn)
+            L.append("  {" + ", ".join(fh(v) for v in row) + "}, \\")
+    L[-1] = L[-1][:-3] + " }"
     for name, hx in consts.items():
         L.append("#define GLIBC_SC_%s %s" % (name.upper(), fh(float.fromhex(hx))))
     with open(out, "w") as f:
