@@ -2,27 +2,40 @@
 """bench.py -- throughput of the sampling hot path (draws/s) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--dist NAME] [--real f64|f32] [--streams S] [--draws D]
-                    [--detail]
+                    [--dist NAME] [--real f64|f32] [--streams-total S | --streams S_PER_GPU]
+                    [--draws D] [--no-detail] [--no-density] [--no-cpu]
 
 One "step" = one launch of the sampler over the whole workload: S streams x D
 draws per stream (monty_random_n_<dist>(D, ..., state), ref: src/random.cpp:
-211-338), output written stream-major to HBM.  The default workload is
-BASELINE.json configs[1]: normal draws, ziggurat, 2^20 streams x 1000 draws,
-double.  Prints ONE JSON line (see the contract in the task statement):
+211-338), output written stream-major to HBM.
 
-  value      whole-job Gdraws/s, inputs and outputs resident in HBM
-  e2e        the same metric through the host-buffer C-ABI call
-             (mb200_rng_sample): parameters copied host->device and all draws
-             copied device->host into pinned memory inside the timed region
-  roofline   algorithmic HBM bytes per launch / CUDA-event kernel time
-             against MEASURED_PEAKS.json's hbm_gbs
-  cpu_baseline  the reference's own CPU code (oracle/_ref, kind "reference";
-             or the C restatement, kind "port") on this box's host cores
+Default workload = BASELINE.json's metric: normal draws (ziggurat, double) over
+2^24 streams IN TOTAL, sharded over the N GPUs by long_jump (each rank holds
+2^24 / N streams: strong scaling), D = 128 draws per stream per launch
+(17.2 GB of output in total; D = 1000 would be 134 GB on one GPU and has no
+host-side end-to-end leg).  `--streams S` switches to S streams PER GPU (weak
+scaling); BASELINE configs[1] (2^20 x 1000) is `--streams 1048576 --draws 1000`
+and is also timed as the first row of `detail`.
+
+Prints ONE JSON line (the contract in the task statement):
+
+  value        whole-job Gdraws/s, inputs and outputs resident in HBM
+  e2e          the same metric through the host-buffer C-ABI call
+               (mb200_rng_sample): parameters copied host->device and all draws
+               copied device->host inside the timed region
+  roofline     algorithmic HBM bytes per launch / CUDA-event kernel time against
+               MEASURED_PEAKS.json's hbm_gbs, plus the pipe fractions of the
+               kernel (instruction counts per draw from profiles/inst_counts.json,
+               one ncu pass; peaks from profiles/pipe_peaks.json)
+  cpu_baseline the reference's own CPU code on this box's host cores
+  density      config C5: fused log-likelihood (Poisson, negative binomial,
+               beta-binomial) of 1e9 observations in total + all-reduce, every N
+  detail       (1 GPU) the other samplers at the C2 / C3 / C4 shapes with the
+               bound that applies to each, and end-to-end legs of C3 / C4
 
 --impl reference runs the reference's CPU implementation only (rank 0).
-Inputs (16 B of scalars) are far smaller than L2; the 8.6 GB of output per
-step is far larger than L2 (126 MB), so no L2 flush is needed between steps.
+Inputs are a few bytes to 0.4 GB, outputs 2-17 GB per step, far larger than L2
+(126 MB), so no L2 flush is needed between steps.
 """
 import argparse
 import json
@@ -34,52 +47,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
 DEFAULT_DIST = "normal_ziggurat"
-N_PARAMS = {"real": 0, "uniform": 2, "exponential_rate": 1, "normal_ziggurat": 2,
-            "normal_box_muller": 2, "normal_polar": 2, "binomial": 2, "poisson": 1,
-            "gamma_scale": 2, "beta": 2, "negative_binomial_prob": 2,
-            "hypergeometric": 3, "truncated_normal": 4}
+STREAMS_TOTAL = 1 << 24
+DRAWS_STRONG = 128
+DRAWS_WEAK = 1000
 
 
-def synthetic_params(dist, n, first_stream=0):
-    """Seed-defined per-stream parameters, identical on CPU and GPU.
-    Scalars where the config uses scalars (C1/C2), vectors for C3/C4."""
-    from oracle_lib import counter_hash
-    idx = np.arange(first_stream, first_stream + n)
-    h = lambda k: counter_hash(idx, k)  # noqa: E731
-    if dist == "real":
-        return []
-    if dist in ("normal_ziggurat", "normal_box_muller", "normal_polar"):
-        return [np.array([0.0]), np.array([1.0])]
-    if dist == "uniform":
-        return [np.array([0.0]), np.array([1.0])]
-    if dist == "exponential_rate":
-        return [np.array([1.0])]
-    if dist == "binomial":
-        return [np.floor(10 ** (6 * h(0))), h(1)]
-    if dist == "poisson":
-        lam = 10 ** (-1 + 5 * h(2))
-        return [np.where(idx % 128 == 0, 1e8 * (1 + h(0)), lam)]
-    if dist == "gamma_scale":
-        return [10 ** (-1 + 2.5 * h(0)), 0.5 + h(1)]
-    if dist == "beta":
-        return [0.2 + 20 * h(0), 0.2 + 20 * h(1)]
-    if dist == "negative_binomial_prob":
-        return [0.5 + 100 * h(0), 0.05 + 0.9 * h(1)]
-    if dist == "hypergeometric":
-        n1 = np.floor(2000 * h(0)); n2 = np.floor(2000 * h(1))
-        return [n1, n2, np.floor((n1 + n2) * h(2))]
-    if dist == "truncated_normal":
-        mn = -3 + 5 * h(0)
-        mx = mn + 0.1 + 4 * h(1)
-        mx = np.where(idx % 8 == 1, np.inf, mx)
-        mn = np.where(idx % 16 == 0, -np.inf, mn)
-        return [np.zeros(n), np.ones(n), mn, mx]
-    raise ValueError(dist)
+def synthetic_params(dist, n, first_stream=0, per_stream_normal=False):
+    from monty_b200.synthetic import sampler_params
+    return sampler_params(dist, n, first_stream, per_stream_normal)
 
 
 def algorithmic_bytes(n_streams, n_draws, params, out_bytes):
@@ -136,9 +115,59 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _load_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    try:
+        with open(p) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def bounds(dist, n_draws, draws_per_s, hbm_gbs, hbm_peak, per_stream=False):
+    """Which resource bounds the kernel: achieved fraction of the measured HBM
+    peak and of each pipe's measured peak (profiles/pipe_peaks.json), from the
+    kernel's warp-instruction counts per draw (profiles/inst_counts.json: one
+    `ncu --metrics smsp__inst_executed*` pass per sampler and shape class,
+    tools/ncu_counts.sh).  `bound` names the largest fraction."""
+    fr = {"hbm": hbm_gbs / hbm_peak}
+    counts = _load_json("inst_counts.json")
+    peaks = _load_json("pipe_peaks.json")
+    key = "%s@%d" % (dist, n_draws) + ("/per_stream" if per_stream else "")
+    c = counts.get(key)
+    if c and peaks:
+        per = {"fp64": ("fp64_per_draw", "dfma_thread_inst_per_s"), "alu": ("alu_per_draw", "alu_thread_inst_per_s"),
+               "fma": ("fma_per_draw", "ffma_thread_inst_per_s"), "issue": ("inst_per_draw", "issue_thread_inst_per_s")}
+        for name, (ck, pk) in per.items():
+            if ck in c and pk in peaks:
+                fr[name] = c[ck] * 32.0 * draws_per_s / peaks[pk]
+    bound = max(fr, key=lambda k: fr[k])
+    out = {"bound": bound, "frac": fr[bound]}
+    out.update({k + "_frac": v for k, v in fr.items()})
+    if c:
+        out["inst_per_draw"] = c.get("inst_per_draw")
+        out["fp64_inst_per_draw"] = c.get("fp64_per_draw")
+        out["lanes_active"] = c.get("lanes_active")
+    else:
+        out["pipe_fractions"] = "no instruction counts for %s in profiles/inst_counts.json" % key
+    return out
+
+
 def cpu_reference_run(dist, real, n_streams, n_draws, steps, warmup, threads=None):
     """Time the reference's CPU implementation (all host threads, OpenMP static
     over streams as in inst/random/openmp/rnguse.cpp:19-24)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle, have_reference
     kind = "reference" if have_reference() else "port"
     orc = Oracle(kind)
@@ -156,37 +185,63 @@ def cpu_reference_run(dist, real, n_streams, n_draws, steps, warmup, threads=Non
     return kind, threads, times
 
 
+def cpu_density_run(name, n_obs, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle, have_reference
+    from monty_b200.synthetic import density_inputs_numpy
+    kind = "reference" if have_reference() else "port"
+    orc = Oracle(kind)
+    x, pars = density_inputs_numpy(name, n_obs)
+    orc.density(name, x[:1000], [p[:1000] for p in pars], True)
+    t0 = time.perf_counter()
+    orc.density(name, x, pars, True)
+    return kind, time.perf_counter() - t0
+
+
+def workload(args, world):
+    """(streams on this GPU's shard description, config dict)."""
+    if args.streams:
+        total = args.streams * world
+        desc = "%d streams per GPU" % args.streams
+        scaling = "weak"
+    else:
+        total = args.streams_total
+        desc = "%d streams in total (%d per GPU)" % (total, total // world)
+        scaling = "strong"
+    out_bytes = 4 if (args.real == "f32" and args.out_f32) else 8
+    cfg = {"workload": "monty_random_n_%s: %s x %d draws/stream, real_type %s, seed 42, long_jump-separated "
+                       "shard per GPU" % (args.dist, desc, args.draws, args.real),
+           "streams_total": total, "streams_per_gpu": total // world, "draws_per_stream": args.draws,
+           "l2": "per-step output per GPU (%.2f GB) >> L2 (126 MB), no flush needed"
+                 % (total // world * args.draws * out_bytes / 1e9)}
+    return total, scaling, cfg
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    # a bounded sample of the same workload: S/64 streams, same draws per stream
-    n_streams = max(1024, args.streams // 64)
+    total, scaling, cfg = workload(args, world)
+    # a bounded sample of the same workload: 1/64 of the streams, same draws per stream
+    n_streams = max(1024, total // 64)
     kind, threads, times = cpu_reference_run(args.dist, args.real, n_streams, args.draws,
                                              args.steps, args.warmup)
     t = float(np.mean(times))
     value = n_streams * args.draws / t / 1e9
     sample = "%d streams x %d draws per step (1/%d of the workload's streams), %d threads" % (
-        n_streams, args.draws, args.streams // n_streams, threads)
+        n_streams, args.draws, total // n_streams, threads)
     line = {
         "impl": "reference", "metric": "Gdraws/s (%s, %s)" % (args.dist, args.real),
         "value": value, "unit": "Gdraws/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "Gdraws/s", "cores": threads, "kind": kind,
+        "scaling": scaling, "vs_baseline": None, "dtype": args.real, "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "Gdraws/s", "cores": threads, "cpu": cpu_model(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "Gdraws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def workload_config(args):
-    return {"workload": "monty_random_n_%s: %d streams x %d draws/stream, real_type %s, seed 42, "
-                        "long_jump-separated shard per GPU" % (args.dist, args.streams, args.draws, args.real),
-            "streams_per_gpu": args.streams, "draws_per_stream": args.draws,
-            "l2": "per-step output (%.2f GB) >> L2, no flush needed" % (
-                args.streams * args.draws * (4 if args.real == "f32" and args.out_f32 else 8) / 1e9)}
 
 
 def time_device(mb, torch, rng, dist, real, n_draws, params_dev, out, steps, warmup, barrier):
@@ -211,109 +266,116 @@ def time_device(mb, torch, rng, dist, real, n_draws, params_dev, out, steps, war
     return total_ms, kernel_ms, wall
 
 
-def density_inputs(torch, name, n, first, dev):
-    """SURVEY 8(d) C5 inputs, generated on the device from the same counter hash."""
-    idx = torch.arange(first, first + n, dtype=torch.int64, device=dev)
-
-    def h(k):
-        m64 = (1 << 64) - 1
-        # splitmix64 on int64 with wrap-around (two's complement == mod 2^64)
-        def c(v):
-            v &= m64
-            return v - (1 << 64) if v >= (1 << 63) else v
-        z = (idx * 8 + k) * 2 + 1
-        z = z * c(0x9E3779B97F4A7C15)
-        z = z ^ c(0xC0FFEE)
-        z = z + c(0x9E3779B97F4A7C15)
-        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * c(0xBF58476D1CE4E5B9)
-        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * c(0x94D049BB133111EB)
-        z = z ^ ((z >> 31) & ((1 << 33) - 1))
-        top = (z >> 11) & ((1 << 53) - 1)
-        return top.to(torch.float64) * 1.1102230246251565e-16 + 1.1102230246251565e-16 / 2.0
-    x = torch.floor(200 * h(0) ** 2).to(torch.int32)
-    if name == "poisson":
-        return x, [0.5 + 100 * h(1)]
-    if name == "negative_binomial_mu":
-        return x, [0.5 + 50 * h(1), 0.1 + 100 * h(2)]
-    size = (x + torch.floor(100 * h(1)).to(torch.int32)).to(torch.int32)
-    return x, [size, 0.05 + 0.9 * h(2), 0.01 + 0.49 * h(3)]
+def host_buffer(torch, shape, want_pinned=True):
+    if want_pinned:
+        try:
+            return torch.empty(shape, dtype=torch.float64, pin_memory=True), True
+        except RuntimeError:            # many ranks on one host can exhaust lockable memory
+            pass
+    return torch.empty(shape, dtype=torch.float64), False
 
 
-def run_density(args, mb, torch, dev, rank, world, local_rank, dist_on, barrier):
+def time_e2e(mb, torch, rng, dist, real, n_streams, n_draws, params, steps, barrier, pinned=True):
+    """Seconds per call of mb200_rng_sample with HOST parameter and output buffers."""
+    import ctypes as C
+    host_out, is_pinned = host_buffer(torch, (n_streams, n_draws), pinned)
+    host_np = host_out.numpy()
+    arrs = [np.ascontiguousarray(p) for p in params]
+    ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs] + [None] * (4 - len(arrs)))
+    lens = (C.c_size_t * 4)(*[a.size for a in arrs] + [0] * (4 - len(arrs)))
+    lib = mb._lib.lib
+    did = mb._lib.DIST[dist]
+    rt = 1 if real == "f32" else 0
+
+    def step():
+        mb._lib.check(lib.mb200_rng_sample(rng.handle, did, rt, n_draws, ptrs, lens,
+                                           C.c_void_p(host_np.ctypes.data)))
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    h2d = int(sum(a.nbytes for a in arrs))
+    d2h = int(n_streams * n_draws * 8)
+    del host_out
+    return dt, is_pinned, h2d, d2h
+
+
+def density_leg(args, mb, torch, dev, rank, world, dist_on, barrier, hbm_peak):
+    """Config C5: per-rank fused log-likelihood + all-reduce of the 8-byte partials."""
     from monty_b200.distributed import density_sum_dev, allreduce_sum
-    n = args.obs
-    x, pars = density_inputs(torch, args.density, n, rank * n, dev)
-    bytes_per_obs = x.element_size() + sum(p.element_size() for p in pars)
-    launches0 = mb._lib.lib.mb200_launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    for _ in range(max(args.warmup, 3)):
-        allreduce_sum(density_sum_dev(args.density, x, pars))
-    torch.cuda.synchronize()
-    barrier()
-    evs = []
-    total = None
-    for _ in range(args.steps):
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        part = density_sum_dev(args.density, x, pars)
-        b.record()
-        total = allreduce_sum(part)
-        c.record()
-        evs.append((a, b, c))
-    torch.cuda.synchronize()
-    barrier()
-    clock_info = clocks.stop()
-    launches = mb._lib.lib.mb200_launch_count() - launches0 - 2 * max(args.warmup, 3)
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b, c in evs]))
-    tot_ms = evs[0][0].elapsed_time(evs[-1][2])
-    t = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
-    if dist_on:
-        import torch.distributed as td
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    peak, peak_src = measured_peak()
-    achieved = n * bytes_per_obs / (k_ms * 1e-3) / 1e9
-    if rank == 0:
-        print(json.dumps({
-            "metric": "Gobs/s (log-density %s, f64, fused sum + all-reduce)" % args.density,
-            "value": world * n / (ms_per_step * 1e-3) / 1e9, "unit": "Gobs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "density::%s log-likelihood, %d observations per GPU, reduce-only"
-                                   % (args.density, n), "l2": "inputs %.1f GB >> L2" % (n * bytes_per_obs / 1e9)},
-            "clocks": clock_info, "gpu_launches": int(launches), "log_likelihood": float(total.item()),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "density_kernel<%s>" % args.density, "kernel_ms": k_ms,
-                         "note": "lgamma-heavy: expected FP64-pipe bound, not HBM bound"}}))
+    from monty_b200.synthetic import density_inputs_torch, DENSITY_BYTES_PER_OBS
+    n_total = args.obs_total
+    lo = rank * (n_total // world)
+    n = n_total // world
+    res = {}
+    for name in ("poisson", "negative_binomial_mu", "beta_binomial_prob"):
+        x, pars = density_inputs_torch(name, n, lo, dev)
+        for _ in range(3):
+            allreduce_sum(density_sum_dev(name, x, pars))
+        torch.cuda.synchronize()
+        barrier()
+        steps = 10
+        evs = []
+        total = None
+        for _ in range(steps):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            part = density_sum_dev(name, x, pars)
+            b.record()
+            total = allreduce_sum(part)
+            c.record()
+            evs.append((a, b, c))
+        torch.cuda.synchronize()
+        barrier()
+        k_ms = float(np.mean([a.elapsed_time(b) for a, b, c in evs]))
+        ar_us = float(np.mean([b.elapsed_time(c) for a, b, c in evs])) * 1e3
+        tot_ms = evs[0][0].elapsed_time(evs[-1][2]) / steps
+        t = torch.tensor([tot_ms, k_ms, ar_us], dtype=torch.float64, device=dev)
+        if dist_on:
+            import torch.distributed as td
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        tot_ms, k_ms, ar_us = (float(v) for v in t.tolist())
+        bpo = DENSITY_BYTES_PER_OBS[name]
+        gbs = n * bpo / (k_ms * 1e-3) / 1e9
+        res[name] = {"gobs_per_s": world * n / (tot_ms * 1e-3) / 1e9, "ms_per_evaluation": tot_ms,
+                     "kernel_ms": k_ms, "allreduce_us": ar_us if dist_on else 0.0,
+                     "observations_total": world * n, "observations_per_gpu": n, "n_gpus": world,
+                     "bytes_per_obs": bpo, "hbm_gbs_per_gpu": gbs, "hbm_frac": gbs / hbm_peak,
+                     "log_likelihood": float(total.item())}
+        del x, pars
+    return res
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dist", default=DEFAULT_DIST)
     ap.add_argument("--real", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--streams", type=int, default=1 << 20)
-    ap.add_argument("--draws", type=int, default=1000)
+    ap.add_argument("--streams-total", dest="streams_total", type=int, default=STREAMS_TOTAL,
+                    help="streams over all GPUs (strong scaling; the default workload)")
+    ap.add_argument("--streams", type=int, default=0, help="streams PER GPU (weak scaling) instead of --streams-total")
+    ap.add_argument("--draws", type=int, default=0, help="draws per stream per launch (default 128; 1000 with --streams)")
+    ap.add_argument("--per-stream-params", action="store_true", help="normal samplers: per-stream mean / sd vectors")
     ap.add_argument("--out-f32", dest="out_f32", action="store_true",
                     help="float32 device output (only with --real f32)")
     ap.add_argument("--detail", action="store_true", help="also time the other distributions (default at 1 GPU)")
     ap.add_argument("--no-detail", dest="no_detail", action="store_true",
                     help="skip the per-distribution table of the default 1-GPU run")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-density", action="store_true", help="skip the config-C5 log-likelihood leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (development)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="sample", choices=["sample", "density"],
-                    help="density: config C5, fused log-likelihood + all-reduce")
-    ap.add_argument("--density", default="poisson",
-                    choices=["poisson", "negative_binomial_mu", "beta_binomial_prob"])
-    ap.add_argument("--obs", type=int, default=125_000_000, help="observations per GPU (density)")
+    ap.add_argument("--obs-total", dest="obs_total", type=int, default=1_000_000_000,
+                    help="observations over all GPUs in the density leg (config C5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if not args.draws:
+        args.draws = DRAWS_WEAK if args.streams else DRAWS_STRONG
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -321,6 +383,7 @@ def main():
 
     import torch
     import monty_b200 as mb
+    from monty_b200.distributed import create_sharded_rng
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -336,17 +399,20 @@ def main():
     else:
         barrier = lambda: None  # noqa: E731
 
-    if args.workload == "density":
-        run_density(args, mb, torch, dev, rank, world, local_rank, dist_on, barrier)
-        if dist_on:
-            td.barrier()
-            td.destroy_process_group()
-        return
-
-    S, D = args.streams, args.draws
-    # shard: GPU g holds S streams of the generator seed(42) long-jumped g times
-    rng = mb.monty_rng_create(S, 42, device=local_rank, long_jumps=rank, real_type=args.real)
-    params = synthetic_params(args.dist, S, first_stream=rank * S)
+    total, scaling, cfg = workload(args, world)
+    D = args.draws
+    # shard: rank r holds its block of streams of the generator seed(42) long-jumped r times
+    # (R/random.R:161-171); no collective on the sampling path
+    if args.streams:
+        S = args.streams
+        first = rank * S
+        rng = mb.monty_rng_create(S, 42, device=local_rank, long_jumps=rank, real_type=args.real)
+    else:
+        from monty_b200.distributed import shard_bounds
+        first, last = shard_bounds(total, rank, world)
+        S = last - first
+        rng = create_sharded_rng(total, 42, rank, world, mode="long_jump", device=local_rank, real_type=args.real)
+    params = synthetic_params(args.dist, S, first_stream=first, per_stream_normal=args.per_stream_params)
     params_dev = [torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in params]
     out_dtype = torch.float32 if (args.real == "f32" and args.out_f32) else torch.float64
     out = torch.empty((S, D), dtype=out_dtype, device=dev)
@@ -364,111 +430,110 @@ def main():
         td.all_reduce(t_local, op=td.ReduceOp.MAX)
     t_ms = float(t_local.item())
     ms_per_step = t_ms / args.steps
-    value = world * S * D / (ms_per_step * 1e-3) / 1e9
+    value = total * D / (ms_per_step * 1e-3) / 1e9
 
-    # roofline of the dominant (only) kernel, per launch
+    # roofline of the dominant (only) kernel, per launch, on this rank's shard
     peak, peak_src = measured_peak()
     alg_bytes = algorithmic_bytes(S, D, params, out.element_size())
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    kernel_name = ("ziggurat_kernel<%s>" % args.real) if (args.dist == "normal_ziggurat" and D >= 2) \
+        else "sample_kernel<%s,%s>" % (args.dist, args.real)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": ("ziggurat_kernel<%s>" % args.real) if (args.dist == "normal_ziggurat" and D >= 2)
-                else "sample_kernel<%s,%s>" % (args.dist, args.real),
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            with open(prof) as fh:
-                tr = json.load(fh).get("%s_%s" % (args.dist, args.real))
-            if tr:
-                roofline["traffic"] = tr
-        except Exception:
-            pass
+                "frac": achieved / peak, "traffic": None, "traffic_source": None, "peak_source": peak_src,
+                "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "launch_shape": "%d streams x %d draws on one GPU" % (S, D)}
+    tr = _load_json("traffic.json").get("%s_%s@%dx%d" % (args.dist, args.real, S, D))
+    if tr:
+        roofline["traffic"] = tr["bytes"]
+        roofline["traffic_source"] = "profiles/traffic.json: %s (static file from one ncu --set full capture of this " \
+                                     "launch shape, NOT measured in this run)" % tr["source"]
+    roofline["pipes"] = bounds(args.dist, D, S * D / (k_ms * 1e-3), achieved, peak, args.per_stream_params)
 
     # end to end through the host-buffer C-ABI call (what the R glue calls)
     e2e = None
-    if rank == 0 or dist_on:
-        try:
-            host_out = torch.empty((S, D), dtype=torch.float64, pin_memory=True)
-            pinned = True
-        except RuntimeError:                     # many ranks on one host can exhaust lockable memory
-            host_out = torch.empty((S, D), dtype=torch.float64)
-            pinned = False
-        host_np = host_out.numpy()
-        import ctypes as C
-        arrs = [np.ascontiguousarray(p) for p in params]
-        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs] + [None] * (4 - len(arrs)))
-        lens = (C.c_size_t * 4)(*[a.size for a in arrs] + [0] * (4 - len(arrs)))
-        lib = mb._lib.lib
-        did = mb._lib.DIST[args.dist]
-        rt = 1 if args.real == "f32" else 0
-
-        def e2e_step():
-            mb._lib.check(lib.mb200_rng_sample(rng.handle, did, rt, D, ptrs, lens,
-                                               C.c_void_p(host_np.ctypes.data)))
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
+    if not args.no_e2e:
+        dt, pinned, h2d, d2h = time_e2e(mb, torch, rng, args.dist, args.real, S, D, params, args.e2e_steps, barrier)
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        flags = [pinned]
         if dist_on:
             td.all_reduce(t_e, op=td.ReduceOp.MAX)
+            flags = [None] * world
+            td.all_gather_object(flags, pinned)
         dt = float(t_e.item())
-        e2e = {"value": world * S * D / dt / 1e9, "unit": "Gdraws/s",
-               "h2d_bytes_per_step": int(sum(a.nbytes for a in arrs)),
-               "d2h_bytes_per_step": int(S * D * 8), "ms_per_step": dt * 1e3,
-               "api": "mb200_rng_sample (host buffers, %s output)" % ("pinned" if pinned else "pageable")}
-        del host_out
+        e2e = {"value": total * D / dt / 1e9, "unit": "Gdraws/s",
+               "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": dt * 1e3,
+               "timed_calls": args.e2e_steps, "pinned_output_per_rank": flags,
+               "api": "mb200_rng_sample (host parameter and output buffers), one call per rank per step"}
+    del out
+
+    # config C5 at every N: fused log-likelihood + all-reduce
+    density = None
+    if not args.no_density:
+        density = density_leg(args, mb, torch, dev, rank, world, dist_on, barrier, peak)
 
     detail = None
     if (args.detail or (world == 1 and not args.no_detail)) and rank == 0:
         detail = {}
-        for name, s_d in [("real", (S, D)), ("uniform", (S, D)), ("exponential_rate", (S, D)),
-                          ("normal_box_muller", (S, D)), ("normal_polar", (S, D)),
-                          ("binomial", (1 << 22, 1)), ("poisson", (1 << 22, 1)),
-                          ("binomial", (1 << 22, 16)), ("poisson", (1 << 22, 16)),
-                          ("gamma_scale", (1 << 21, 16)), ("beta", (1 << 21, 16)),
-                          ("negative_binomial_prob", (1 << 21, 16)), ("hypergeometric", (1 << 21, 16)),
-                          ("truncated_normal", (1 << 21, 16))]:
-            s2, d2 = s_d
+        c2 = (1 << 20, 1000)
+        rows = [("normal_ziggurat", c2, False), ("normal_ziggurat", c2, True),
+                ("real", c2, False), ("uniform", c2, False), ("exponential_rate", c2, False),
+                ("normal_box_muller", c2, False), ("normal_polar", c2, False),
+                ("binomial", (1 << 22, 1), False), ("poisson", (1 << 22, 1), False),
+                ("binomial", (1 << 22, 16), False), ("poisson", (1 << 22, 16), False),
+                ("gamma_scale", (1 << 21, 16), False), ("beta", (1 << 21, 16), False),
+                ("negative_binomial_prob", (1 << 21, 16), False), ("hypergeometric", (1 << 21, 16), False),
+                ("truncated_normal", (1 << 21, 16), False)]
+        for name, (s2, d2), per_stream in rows:
             r2 = mb.monty_rng_create(s2, 42, device=local_rank, real_type=args.real)
-            p2 = synthetic_params(name, s2)
+            p2 = synthetic_params(name, s2, per_stream_normal=per_stream)
             p2d = [torch.from_numpy(np.ascontiguousarray(p)).to(dev) for p in p2]
             o2 = torch.empty((s2, d2), dtype=torch.float64, device=dev)
             tm, km, _ = time_device(mb, torch, r2, name, args.real, d2, p2d, o2, 5, 3, lambda: None)
             kms = float(np.mean(km))
             ab = algorithmic_bytes(s2, d2, p2, 8)
-            detail["%s[%dx%d]" % (name, s2, d2)] = {
-                "gdraws_per_s": s2 * d2 / (kms * 1e-3) / 1e9, "kernel_ms": kms,
-                "hbm_gbs": ab / (kms * 1e-3) / 1e9, "hbm_frac": ab / (kms * 1e-3) / 1e9 / peak}
+            gbs = ab / (kms * 1e-3) / 1e9
+            row = {"gdraws_per_s": s2 * d2 / (kms * 1e-3) / 1e9, "kernel_ms": kms, "hbm_gbs": gbs}
+            row.update(bounds(name, d2, s2 * d2 / (kms * 1e-3), gbs, peak, per_stream))
+            if d2 <= 16 and name in ("binomial", "poisson", "gamma_scale", "hypergeometric") and not args.no_e2e:
+                # the shapes the R API is called in a loop with: host vectors up, draws down
+                for pin in (True, False):
+                    dt, was, h2d, d2h = time_e2e(mb, torch, r2, name, args.real, s2, d2, p2, 10, lambda: None, pin)
+                    row["e2e_%s" % ("pinned" if was else "pageable")] = {
+                        "gdraws_per_s": s2 * d2 / dt / 1e9, "ms_per_call": dt * 1e3, "timed_calls": 10,
+                        "h2d_bytes": h2d, "d2h_bytes": d2h}
+            detail["%s[%dx%d]%s" % (name, s2, d2, " per-stream mean/sd" if per_stream else "")] = row
             r2.close()
             del o2
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = max(1024, S // 8)       # ~10 core-seconds of CPU work over the three repeats
+        n_cpu = max(1024, total // 128)       # ~10 core-seconds of CPU work over the three repeats
         kind, threads, times = cpu_reference_run(args.dist, args.real, n_cpu, D, 3, 1)
         tcpu = float(np.mean(times))
         kind1, _, times1 = cpu_reference_run(args.dist, args.real, n_cpu // 8, D, 2, 1, threads=1)
-        cpu = {"value": n_cpu * D / tcpu / 1e9, "unit": "Gdraws/s", "cores": threads, "kind": kind,
+        cpu = {"value": n_cpu * D / tcpu / 1e9, "unit": "Gdraws/s", "cores": threads, "cpu": cpu_model(), "kind": kind,
                "sample": "%d streams x %d draws (1/%d of the workload), OpenMP static over streams"
-                         % (n_cpu, D, S // n_cpu),
+                         % (n_cpu, D, total // n_cpu),
                "single_thread_value": (n_cpu // 8) * D / float(np.mean(times1)) / 1e9}
+        if density:
+            for name in density:
+                kd, td_s = cpu_density_run(name, 2_000_000)
+                density[name]["cpu_gobs_per_s_single_thread"] = 2_000_000 / td_s / 1e9
 
     if rank == 0:
         line = {
             "metric": "Gdraws/s (%s, %s)" % (args.dist, args.real), "value": value,
             "unit": "Gdraws/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": args.real, "data": "synthetic",
-            "config": workload_config(args), "clocks": clock_info,
+            "config": cfg, "clocks": clock_info,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if density:
+            line["density"] = density
         if detail:
             line["detail"] = detail
         print(json.dumps(line))

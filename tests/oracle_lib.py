@@ -240,14 +240,15 @@ class Oracle:
         return out
 
 
-def counter_hash(i, k):
-    """The seed-defined parameter hash of SURVEY 8(d): h(i, k) in (0, 1).
-    h = int_to_real<double>(splitmix64(0x9E3779B97F4A7C15*(2*(i*8+k)+1) ^ 0xC0FFEE))."""
-    i = np.asarray(i, dtype=np.uint64)
-    with np.errstate(over="ignore"):
-        z = (np.uint64(0x9E3779B97F4A7C15) * (np.uint64(2) * (i * np.uint64(8) + np.uint64(k)) + np.uint64(1))) ^ np.uint64(0xC0FFEE)
-        z = z + np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    return (z >> np.uint64(11)).astype(np.float64) * 1.1102230246251565e-16 + 1.1102230246251565e-16 / 2.0
+def _load_synthetic():
+    """monty_b200/synthetic.py (pure numpy) loaded by path, so that the oracle's
+    helpers do not import the product package (and its kernel library)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_mb200_synthetic", os.path.join(ROOT, "monty_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+synthetic = _load_synthetic()
+counter_hash = synthetic.counter_hash

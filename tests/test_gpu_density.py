@@ -130,12 +130,12 @@ def test_device_resident_sum_and_bench_inputs(mb, oracle):
     import os, sys
     import torch
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import bench
+    from monty_b200.synthetic import density_inputs_torch
     from monty_b200.distributed import density_sum_dev
     dev = torch.device("cuda", 0)
     n = 200000
     for name in ("poisson", "negative_binomial_mu", "beta_binomial_prob"):
-        x, pars = bench.density_inputs(torch, name, n, 1000, dev)
+        x, pars = density_inputs_torch(name, n, 1000, dev, chunk=65536)
         from oracle_lib import counter_hash
         idx = np.arange(1000, 1000 + n)
         assert np.array_equal(x.cpu().numpy(), np.floor(200 * counter_hash(idx, 0) ** 2).astype(np.int32))

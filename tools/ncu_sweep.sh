@@ -3,9 +3,9 @@
 set -x
 run() {  # name dist streams draws extra...
   name=$1; shift
-  python bench.py --steps 2 --warmup 1 --no-cpu --no-detail --e2e-steps 1 "$@" > gpurun_out/plain_$name.log 2>&1 &&
+  python bench.py --steps 2 --warmup 1 --no-cpu --no-detail --no-density --no-e2e "$@" > gpurun_out/plain_$name.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:"sample_kernel|density_kernel" -s 1 -c 1 -f \
-      -o gpurun_out/prof_r01_$name python bench.py --steps 2 --warmup 1 --no-cpu --no-detail --e2e-steps 1 "$@" > gpurun_out/ncu_$name.log 2>&1
+      -o gpurun_out/prof_r01_$name python bench.py --steps 2 --warmup 1 --no-cpu --no-detail --no-density --no-e2e "$@" > gpurun_out/ncu_$name.log 2>&1
   # the reports are too big to bring back together (64 MiB limit): summarise on the box
   python tools/ncu_summary.py gpurun_out/prof_r01_$name.ncu-rep 30 > gpurun_out/r01_${name}_ncu_summary.txt 2>&1
   rm -f gpurun_out/prof_r01_$name.ncu-rep
