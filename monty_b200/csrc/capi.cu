@@ -673,7 +673,7 @@ int mb200_density_dev(int dens, int real_type, size_t n,
   a.out = out_dev;
   a.n = n;
   a.log = log;
-  const int grid = density_grid(n, sm);
+  int grid = density_max_partials(sm);
   double* partial = nullptr;
   bool pooled = false;
   if (sum_dev) {
@@ -687,7 +687,7 @@ int mb200_density_dev(int dens, int real_type, size_t n,
     a.partial = partial;
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  CU(launch_density(dens, real_type, a, grid, st));
+  CU(launch_density(dens, real_type, a, sm, &grid, st));
   if (sum_dev) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CU(launch_reduce_partials(partial, grid, sum_dev, st));

@@ -14,6 +14,8 @@
 #include "density_dispatch.h"
 #include "launch_args.h"
 
+#include <cstdlib>
+
 namespace mb200 {
 
 constexpr int kDensBlock = 256;
@@ -124,6 +126,183 @@ density_kernel(const DensityArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// The tiled kernel: the path the reference's own call shapes take.
+//
+// ref: src/density.cpp passes x and the size-like arguments of the count
+// densities as cpp11::integers and everything else as doubles -- the "canonical"
+// layout of each density (DensCanon).  With it the element types are compile-
+// time facts, a CTA owns TILES of 1024 consecutive observations (thread t the
+// four observations 4t .. 4t + 3, read with one 128-bit shared load per int32
+// array and two per double array), and the tiles arrive by 1-D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx) into a ring of kDensStages shared
+// buffers: one thread arms the stage's mbarrier with the byte count and issues
+// one copy per argument array; the copy of tile k + kDensStages is in flight
+// while tile k is evaluated.  No registers are spent on prefetching (the
+// register double buffer of round 1 cost a CTA per SM) and the loads no longer
+// stall the warps that issue them (round 1: long-scoreboard 5.6 per issue on
+// scalar 4 / 8-byte loads of four separate sectors per thread).
+//
+// The last, partial tile is read with plain loads.  Per-thread order, the block
+// tree and the order of the partials are fixed: the sum is reproducible.
+// ---------------------------------------------------------------------------
+constexpr int kDensTile = 4 * kDensBlock;     // observations per tile
+constexpr int kDensStages = 3;
+
+// bit 0: x is int32; bit k + 1: parameter k is int32 (ref: src/density.cpp signatures)
+template <int DENS> struct DensCanon {
+  static constexpr unsigned mask =
+    (DENS == MB200_DENS_BINOMIAL || DENS == MB200_DENS_BETA_BINOMIAL_PROB || DENS == MB200_DENS_BETA_BINOMIAL_AB) ? 0x3u :
+    (DENS == MB200_DENS_HYPERGEOMETRIC) ? 0xFu :
+    (DENS == MB200_DENS_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_NEGATIVE_BINOMIAL_PROB || DENS == MB200_DENS_POISSON ||
+     DENS == MB200_DENS_ZI_POISSON || DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_MU ||
+     DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_PROB) ? 0x1u : 0x0u;
+  static constexpr int n_arrays = 1 + DensNP<DENS>::value;
+  __host__ __device__ static constexpr bool is_int(int j) { return (mask >> j) & 1u; }
+  __host__ __device__ static constexpr unsigned tile_bytes(int j) { return kDensTile * (is_int(j) ? 4u : 8u); }
+  __host__ __device__ static constexpr unsigned offset(int j) {       // of array j inside a stage
+    unsigned o = 0;
+    for (int i = 0; i < j; ++i) o += tile_bytes(i);
+    return o;
+  }
+  static constexpr unsigned stage_bytes = offset(n_arrays);
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile("{\n\t"
+               ".reg .pred p;\n\t"
+               "MB200_WAIT:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@p bra MB200_DONE;\n\t"
+               "bra MB200_WAIT;\n\t"
+               "MB200_DONE:\n\t"
+               "}" :: "r"(mbar), "r"(parity) : "memory");
+}
+
+// four consecutive elements of array j for this thread, as T
+// (is_int is a compile-time fact after unrolling)
+template <typename T>
+__device__ __forceinline__ void lds_four(uint32_t saddr, bool is_int, T (&v)[4]) {
+  if (is_int) {
+    int4 q;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(saddr));
+    v[0] = static_cast<T>(q.x); v[1] = static_cast<T>(q.y); v[2] = static_cast<T>(q.z); v[3] = static_cast<T>(q.w);
+  } else {
+    const double2 a = lds_f64x2(saddr), b = lds_f64x2(saddr + 16);
+    v[0] = static_cast<T>(a.x); v[1] = static_cast<T>(a.y); v[2] = static_cast<T>(b.x); v[3] = static_cast<T>(b.y);
+  }
+}
+
+template <int DENS, typename T>
+__global__ void __launch_bounds__(kDensBlock)
+density_tile_kernel(const DensityArgs a, const unsigned long long n_full_tiles) {
+  using Cn = DensCanon<DENS>;
+  constexpr int NPD = DensNP<DENS>::value;
+  constexpr int NA = Cn::n_arrays;
+  extern __shared__ __align__(128) unsigned char dens_smem[];
+  __shared__ __align__(8) unsigned long long mbar_store[kDensStages];
+  const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(dens_smem));
+  const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(mbar_store));
+  const int tid = threadIdx.x;
+  const bool lg = a.log != 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kDensStages; ++s) mbar_init(mbar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const void* src[NA];
+  src[0] = a.x;
+#pragma unroll
+  for (int k = 0; k < NPD; ++k) src[k + 1] = a.par[k];
+
+  auto issue = [&](unsigned long long tile, int s) {
+    if (tid == 0 && tile < n_full_tiles) {
+      const uint32_t mb = mbar0 + 8 * s;
+      // the stage was read through the generic proxy; order those reads before the bulk writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(mb, Cn::stage_bytes);
+#pragma unroll
+      for (int j = 0; j < NA; ++j) {
+        const unsigned long long byte0 = tile * Cn::tile_bytes(j);
+        bulk_copy_g2s(smem0 + s * Cn::stage_bytes + Cn::offset(j), static_cast<const char*>(src[j]) + byte0,
+                      Cn::tile_bytes(j), mb);
+      }
+    }
+  };
+
+  const unsigned long long step = gridDim.x;
+#pragma unroll
+  for (int s = 0; s < kDensStages; ++s) issue(blockIdx.x + s * step, s);
+
+  double acc = 0.0;
+  unsigned it = 0;
+  for (unsigned long long tile = blockIdx.x; tile < n_full_tiles; tile += step, ++it) {
+    const int s = static_cast<int>(it % kDensStages);
+    mbar_wait(mbar0 + 8 * s, (it / kDensStages) & 1u);
+    const uint32_t base = smem0 + s * Cn::stage_bytes;
+    T x[4], p[NPD > 0 ? NPD : 1][4];
+    lds_four<T>(base + Cn::offset(0) + tid * (Cn::is_int(0) ? 16 : 32), Cn::is_int(0), x);
+#pragma unroll
+    for (int k = 0; k < NPD; ++k) {
+      lds_four<T>(base + Cn::offset(k + 1) + tid * (Cn::is_int(k + 1) ? 16 : 32), Cn::is_int(k + 1), p[k]);
+    }
+    __syncthreads();                        // every thread holds its observations: the stage is free
+    issue(tile + kDensStages * step, s);
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      T pu[NPD > 0 ? NPD : 1];
+#pragma unroll
+      for (int k = 0; k < NPD; ++k) pu[k] = p[k][u];
+      v[u] = static_cast<double>(density_compute<DENS, T>(x[u], pu, lg));
+      acc += v[u];
+    }
+    if (a.out) {
+      double2* o = reinterpret_cast<double2*>(a.out + tile * kDensTile + 4 * tid);
+      o[0] = make_double2(v[0], v[1]);
+      o[1] = make_double2(v[2], v[3]);
+    }
+  }
+  // the partial last tile: plain loads, by the block whose turn it would be
+  const unsigned long long tail0 = n_full_tiles * kDensTile;
+  if (tail0 < a.n && blockIdx.x == n_full_tiles % gridDim.x) {
+    for (unsigned long long i = tail0 + tid; i < a.n; i += kDensBlock) {
+      const T x = ld_arg<T>(a.x, Cn::is_int(0), i);
+      T pu[NPD > 0 ? NPD : 1];
+#pragma unroll
+      for (int k = 0; k < NPD; ++k) pu[k] = ld_arg<T>(a.par[k], Cn::is_int(k + 1), i);
+      const double v = static_cast<double>(density_compute<DENS, T>(x, pu, lg));
+      if (a.out) a.out[i] = v;
+      acc += v;
+    }
+  }
+  if (a.partial) {
+    __shared__ double warp_sum[kDensBlock / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) warp_sum[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < kDensBlock / 32; ++w) sum += warp_sum[w];
+      a.partial[blockIdx.x] = sum;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ sum) {
   __shared__ double sh[256];
@@ -144,16 +323,62 @@ int density_grid(unsigned long long n, int sm_count) {
   return static_cast<int>(need < cap ? (need ? need : 1) : cap);
 }
 
+// the reference's own argument types, 16-byte aligned arrays, at least one full tile
 template <int DENS>
-static cudaError_t launch_density_t(int real_type, const DensityArgs& a, int grid, cudaStream_t st) {
+static bool tiled_applies(const DensityArgs& a) {
+  using Cn = DensCanon<DENS>;
+  // the densities that evaluate lgamma of non-integer arguments are FP64-pipe
+  // bound, not load bound: four observations per thread cost them registers and
+  // a CTA per SM (negative binomial 39.3 -> 33.1, beta-binomial 14.2 -> 12.6 Gobs/s)
+  if (DensUnroll<DENS>::value != 4) return false;
+  if (a.n < static_cast<unsigned long long>(kDensTile)) return false;
+  auto ok = [](const void* p, int is_i32, bool want_int) {
+    return (is_i32 != 0) == want_int && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+  };
+  if (!ok(a.x, a.x_is_i32, Cn::is_int(0))) return false;
+  for (int k = 0; k < DensNP<DENS>::value; ++k) {
+    if (!ok(a.par[k], a.par_is_i32[k], Cn::is_int(k + 1))) return false;
+  }
+  return a.out == nullptr || (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+}
+
+template <int DENS, typename T>
+static cudaError_t launch_tiled(const DensityArgs& a, int sm_count, int* grid_out, cudaStream_t st) {
+  using Cn = DensCanon<DENS>;
+  const size_t smem = static_cast<size_t>(Cn::stage_bytes) * kDensStages;
+  const unsigned long long n_full = a.n / kDensTile;
+  // CTAs per SM: as many as shared memory holds (200 KB budget), at most 6
+  int per_sm = static_cast<int>((200u * 1024u) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+  unsigned long long grid = static_cast<unsigned long long>(sm_count) * per_sm;
+  if (grid > n_full) grid = n_full;
+  cudaError_t e = cudaFuncSetAttribute(density_tile_kernel<DENS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  density_tile_kernel<DENS, T><<<static_cast<unsigned>(grid), kDensBlock, smem, st>>>(a, n_full);
+  *grid_out = static_cast<int>(grid);
+  return cudaGetLastError();
+}
+
+template <int DENS>
+static cudaError_t launch_density_t(int real_type, const DensityArgs& a, int sm_count, int* grid_out, cudaStream_t st) {
+  static const bool generic_only = std::getenv("MB200_DENSITY_GENERIC") != nullptr;      // A/B measurements
+  if (!generic_only && tiled_applies<DENS>(a)) {
+    return real_type == MB200_REAL_F32 ? launch_tiled<DENS, float>(a, sm_count, grid_out, st)
+                                       : launch_tiled<DENS, double>(a, sm_count, grid_out, st);
+  }
+  const int grid = density_grid(a.n, sm_count);
+  *grid_out = grid;
   if (real_type == MB200_REAL_F32) density_kernel<DENS, float><<<grid, kDensBlock, 0, st>>>(a);
   else density_kernel<DENS, double><<<grid, kDensBlock, 0, st>>>(a);
   return cudaGetLastError();
 }
 
-cudaError_t launch_density(int dens, int real_type, const DensityArgs& a, int grid, cudaStream_t st) {
+// Launches the density kernel; *grid_out = number of per-block partials written
+// (a.partial must hold density_max_partials(sm_count) doubles).
+cudaError_t launch_density(int dens, int real_type, const DensityArgs& a, int sm_count, int* grid_out, cudaStream_t st) {
   switch (dens) {
-#define C(id) case id: return launch_density_t<id>(real_type, a, grid, st)
+#define C(id) case id: return launch_density_t<id>(real_type, a, sm_count, grid_out, st)
     C(MB200_DENS_BINOMIAL); C(MB200_DENS_NORMAL); C(MB200_DENS_NEGATIVE_BINOMIAL_MU);
     C(MB200_DENS_NEGATIVE_BINOMIAL_PROB); C(MB200_DENS_BETA_BINOMIAL_PROB);
     C(MB200_DENS_BETA_BINOMIAL_AB); C(MB200_DENS_POISSON); C(MB200_DENS_UNIFORM);
@@ -166,6 +391,8 @@ cudaError_t launch_density(int dens, int real_type, const DensityArgs& a, int gr
   default: return cudaErrorInvalidValue;
   }
 }
+
+int density_max_partials(int sm_count) { return sm_count * 8; }
 
 cudaError_t install_lgamma_table_density(const double* d, const float* f) { return lgt_install(d, f); }
 

@@ -41,6 +41,13 @@
 #ifndef MB200_ZIG_UNROLL
 #define MB200_ZIG_UNROLL 4
 #endif
+// MEASUREMENT ONLY (never the shipped build): 1 = every attempt is accepted and the
+// wedge machinery is compiled out -- the bare "next + convert + gather + multiply +
+// compare + store + write-out" loop, whose throughput bounds what any scheduling of
+// the wedge events could reach with this tile / table design (WRONG draws)
+#ifndef MB200_ZIG_BARE
+#define MB200_ZIG_BARE 0
+#endif
 
 namespace mb200 {
 
@@ -189,14 +196,25 @@ __device__ __forceinline__ void zig_word(ZigLane<T, OutT>& L, uint32_t zig_saddr
   }
   const uint32_t idx = ((vlo << 4) & 0x7f80u) | lane_off;    // ((v >> 3) & 255) * 128 + copy * 16
   const double2 xy = lds_f64x2(zig_saddr + idx);
+#if MB200_ZIG_BARE
+  const bool inside = fabs(u0) < xy.y * 4.0;        // always true: the compare is kept, its outcome is not
+  const bool fast = inside;
+  const bool park = false;
+  L.wedge = false;
+#else
   const bool inside = fabs(u0) < xy.y;
   const bool fast = !L.wedge && inside;
   const bool park = !L.wedge && !inside;
+#endif
   const double zx = u0 * xy.x;
   const T zt = static_cast<T>(zx);
   const OutT fy = static_cast<OutT>(STANDARD ? zt : zt * L.sd + L.mean);
   if (!L.wedge) sts_out(L.p, fy);
 
+#if MB200_ZIG_BARE
+  if (fast) L.p = bump(L.p, sizeof(OutT));
+  return;
+#endif
   // 23-bit image of the word: m = 1 + floor(hi / 2^9) / 2^23 in [1, 2)
   const float m = __uint_as_float(__umulhi(vhi, 1u << 23) + 0x3f800000u);
   // the parked candidate against this word (used only when L.wedge)
