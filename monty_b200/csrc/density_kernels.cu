@@ -133,8 +133,9 @@ density_kernel(const DensityArgs a) {
 // densities as cpp11::integers and everything else as doubles -- the "canonical"
 // layout of each density (DensCanon).  With it the element types are compile-
 // time facts, a CTA owns TILES of 1024 consecutive observations (thread t the
-// four observations 4t .. 4t + 3, read with one 128-bit shared load per int32
-// array and two per double array), and the tiles arrive by 1-D TMA bulk copies
+// observations 2t, 2t + 1 of each half of the tile, read with two 128-bit shared
+// loads per double array and two 64-bit ones per int32 array, conflict free),
+// and the tiles arrive by 1-D TMA bulk copies
 // (cp.async.bulk ... mbarrier::complete_tx) into a ring of kDensStages shared
 // buffers: one thread arms the stage's mbarrier with the byte count and issues
 // one copy per argument array; the copy of tile k + kDensStages is in flight
@@ -189,17 +190,61 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
                "}" :: "r"(mbar), "r"(parity) : "memory");
 }
 
-// four consecutive elements of array j for this thread, as T
+// This thread's four observations of one argument array, as T: elements 2t, 2t + 1
+// of each half of the tile -- consecutive lanes read consecutive 16-byte (double) or
+// 8-byte (int32) units, so the shared loads are bank-conflict free (four consecutive
+// doubles per thread are a 32-byte stride: two wavefronts per load).
 // (is_int is a compile-time fact after unrolling)
 template <typename T>
-__device__ __forceinline__ void lds_four(uint32_t saddr, bool is_int, T (&v)[4]) {
+__device__ __forceinline__ void lds_four(uint32_t array_saddr, int tid, bool is_int, T (&v)[4]) {
   if (is_int) {
-    int4 q;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(saddr));
-    v[0] = static_cast<T>(q.x); v[1] = static_cast<T>(q.y); v[2] = static_cast<T>(q.z); v[3] = static_cast<T>(q.w);
-  } else {
-    const double2 a = lds_f64x2(saddr), b = lds_f64x2(saddr + 16);
+    int2 a, b;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(array_saddr + tid * 8));
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(b.x), "=r"(b.y) : "r"(array_saddr + (kDensTile / 2) * 4 + tid * 8));
     v[0] = static_cast<T>(a.x); v[1] = static_cast<T>(a.y); v[2] = static_cast<T>(b.x); v[3] = static_cast<T>(b.y);
+  } else {
+    const double2 a = lds_f64x2(array_saddr + tid * 16), b = lds_f64x2(array_saddr + (kDensTile / 2) * 8 + tid * 16);
+    v[0] = static_cast<T>(a.x); v[1] = static_cast<T>(a.y); v[2] = static_cast<T>(b.x); v[3] = static_cast<T>(b.y);
+  }
+}
+
+// Four observations at once.  Default: four calls.  Poisson in double (config C5's
+// load-bound density) interleaves them: the four lgamma look-ups are issued
+// together and the four logs run as one batch (independent chains hide the table
+// latency; the window around 1 is worked off jointly) -- the same operations on
+// the same values as four calls of dens_poisson (hdr/density.hpp:173-189).
+template <int DENS, typename T, int NPD>
+__device__ __forceinline__ void density_compute4(const T (&x)[4], const T (&p)[NPD > 0 ? NPD : 1][4], bool lg, double (&v)[4]) {
+  if constexpr (DENS == MB200_DENS_POISSON && sizeof(T) == 8) {
+    double lgm[4], ll[4];
+    bool plain = true;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lgm[u] = m_lgamma(x[u] + 1);
+      const uint64_t ix = glibc::f_bits(p[0][u]);
+      plain = plain && (ix - 0x0010000000000000ull < 0x7fe0000000000000ull);      // positive, finite, normal
+    }
+    if (plain) {
+      double lam[4] = {p[0][0], p[0][1], p[0][2], p[0][3]};
+      m_log_normal_batch<4>(lam, ll);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ll[u] = m_log(p[0][u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double ret = x[u] * ll[u] - p[0][u] - lgm[u];
+      if (x[u] == 0 && p[0][u] == 0) ret = 0;
+      v[u] = maybe_log(ret, lg);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      T pu[NPD > 0 ? NPD : 1];
+#pragma unroll
+      for (int k = 0; k < NPD; ++k) pu[k] = p[k][u];
+      v[u] = static_cast<double>(density_compute<DENS, T>(x[u], pu, lg));
+    }
   }
 }
 
@@ -253,26 +298,19 @@ density_tile_kernel(const DensityArgs a, const unsigned long long n_full_tiles) 
     mbar_wait(mbar0 + 8 * s, (it / kDensStages) & 1u);
     const uint32_t base = smem0 + s * Cn::stage_bytes;
     T x[4], p[NPD > 0 ? NPD : 1][4];
-    lds_four<T>(base + Cn::offset(0) + tid * (Cn::is_int(0) ? 16 : 32), Cn::is_int(0), x);
+    lds_four<T>(base + Cn::offset(0), tid, Cn::is_int(0), x);
 #pragma unroll
-    for (int k = 0; k < NPD; ++k) {
-      lds_four<T>(base + Cn::offset(k + 1) + tid * (Cn::is_int(k + 1) ? 16 : 32), Cn::is_int(k + 1), p[k]);
-    }
+    for (int k = 0; k < NPD; ++k) lds_four<T>(base + Cn::offset(k + 1), tid, Cn::is_int(k + 1), p[k]);
     __syncthreads();                        // every thread holds its observations: the stage is free
     issue(tile + kDensStages * step, s);
     double v[4];
+    density_compute4<DENS, T, NPD>(x, p, lg, v);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      T pu[NPD > 0 ? NPD : 1];
-#pragma unroll
-      for (int k = 0; k < NPD; ++k) pu[k] = p[k][u];
-      v[u] = static_cast<double>(density_compute<DENS, T>(x[u], pu, lg));
-      acc += v[u];
-    }
+    for (int u = 0; u < 4; ++u) acc += v[u];
     if (a.out) {
-      double2* o = reinterpret_cast<double2*>(a.out + tile * kDensTile + 4 * tid);
-      o[0] = make_double2(v[0], v[1]);
-      o[1] = make_double2(v[2], v[3]);
+      double* o = a.out + tile * kDensTile + 2 * tid;
+      *reinterpret_cast<double2*>(o) = make_double2(v[0], v[1]);
+      *reinterpret_cast<double2*>(o + kDensTile / 2) = make_double2(v[2], v[3]);
     }
   }
   // the partial last tile: plain loads, by the block whose turn it would be
