@@ -45,11 +45,18 @@ int mb200_example_inline_multinomial(mb200_rng* rng, int real_type,
                                      const double* prob_host, int prob_len, size_t prob_cols,
                                      double* out_host);
 
-/* Evaluates one of the samplers' own math routines (csrc/samplers.cuh) on n
+/* Evaluates one of the samplers' own math routines (include/monty_b200/detail/samplers.cuh) on n
  * host doubles, for the parity tests: fn 0 = m_log, 1 = m_log_normal
  * (positive normal arguments), 2 = cos_0_2pi (0 <= x <= 2 pi), 3 = sqrt_normal
- * (positive normal arguments), 4 = the toolkit's sqrt. */
+ * (positive normal arguments), 4 = the toolkit's sqrt, 5 = 1.0 when the examples
+ * library was compiled without FMA contraction (monty::random::contraction_is_off). */
 int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n);
+
+/* monty::density::zi_poisson (which = 0; a = lambda), zi_negative_binomial_prob
+ * (1; a = size, b = prob), zi_negative_binomial_mu (2; a = size, b = mu) through
+ * the device-side API, elementwise on n host doubles. */
+int mb200_example_zi_density(int which, const double* x_host, const double* pi0_host, const double* a_host,
+                             const double* b_host, int lg, double* y_host, size_t n);
 
 #ifdef __cplusplus
 }

@@ -170,6 +170,7 @@ __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* 
     case 2: r = mb200::cos_0_2pi(v); break;
     case 3: r = mb200::sqrt_normal(v); break;
     case 4: r = sqrt(v); break;
+    case 5: r = monty::random::contraction_is_off() ? 1.0 : 0.0; break;
     default: r = 0.0; break;
   }
   y[i] = r;
@@ -177,7 +178,7 @@ __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* 
 }  // namespace
 
 extern "C" int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n) {
-  if (!x_host || !y_host || fn < 0 || fn > 4) return MB200_ERR_ARG;
+  if (!x_host || !y_host || fn < 0 || fn > 5) return MB200_ERR_ARG;
   double *dx = nullptr, *dy = nullptr;
   int rc = MB200_OK;
   if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&dy, n * sizeof(double)) != cudaSuccess ||
@@ -192,5 +193,42 @@ extern "C" int mb200_example_math_probe(int fn, const double* x_host, double* y_
   }
   if (dx) cudaFree(dx);
   if (dy) cudaFree(dy);
+  return rc;
+}
+
+// ---- monty::density::zi_* through the device-side API ---------------------------
+namespace {
+__global__ void zi_density_kernel(int which, const double* __restrict__ x, const double* __restrict__ pi0,
+                                  const double* __restrict__ a, const double* __restrict__ b, int lg,
+                                  double* __restrict__ y, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r;
+  switch (which) {
+    case 0: r = monty::density::zi_poisson<double>(x[i], pi0[i], a[i], lg != 0); break;
+    case 1: r = monty::density::zi_negative_binomial_prob<double>(x[i], pi0[i], a[i], b[i], lg != 0); break;
+    default: r = monty::density::zi_negative_binomial_mu<double>(x[i], pi0[i], a[i], b[i], lg != 0); break;
+  }
+  y[i] = r;
+}
+}  // namespace
+
+extern "C" int mb200_example_zi_density(int which, const double* x_host, const double* pi0_host, const double* a_host,
+                                        const double* b_host, int lg, double* y_host, size_t n) {
+  if (!x_host || !pi0_host || !a_host || !y_host || which < 0 || which > 2 || (which > 0 && !b_host)) return MB200_ERR_ARG;
+  double* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const double* h[4] = {x_host, pi0_host, a_host, b_host ? b_host : a_host};
+  int rc = MB200_OK;
+  for (int k = 0; k < 5 && rc == MB200_OK; ++k) {
+    if (cudaMalloc(&d[k], n * sizeof(double)) != cudaSuccess) rc = MB200_ERR_CUDA;
+    else if (k < 4 && cudaMemcpy(d[k], h[k], n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = MB200_ERR_CUDA;
+  }
+  if (rc == MB200_OK) {
+    zi_density_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(which, d[0], d[1], d[2], d[3], lg, d[4], n);
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpy(y_host, d[4], n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      rc = MB200_ERR_CUDA;
+    }
+  }
+  for (int k = 0; k < 5; ++k) if (d[k]) cudaFree(d[k]);
   return rc;
 }

@@ -225,7 +225,13 @@ int mb200_rng_sample(mb200_rng* rng, int dist, int real_type, size_t n_samples,
  * out_f32 != 0 (only allowed with MB200_REAL_F32).  Asynchronous on the
  * handle's stream; parameter errors are reported by the next
  * mb200_rng_sync().  Invalid streams are skipped (state untouched, output
- * NaN); all valid streams advance. */
+ * NaN); all valid streams advance.
+ * Ordering contract: the launch is ordered on the handle's own non-blocking
+ * stream (mb200_rng_cuda_stream) and on nothing else.  A caller that produces
+ * params_dev or consumes out_dev on another stream must order the two itself
+ * (an event recorded on the producer stream and waited on by the handle's
+ * stream before the call; the reverse after it) -- monty_b200/random.py's
+ * sample_dev does exactly that with torch's current stream. */
 int mb200_rng_sample_dev(mb200_rng* rng, int dist, int real_type,
                          size_t n_samples,
                          const double* const* params_dev,

@@ -18,7 +18,7 @@
 //
 // Every function draws from the caller's state exactly the words the
 // reference draws, in the same order, and computes the same operations in the
-// same order (csrc/samplers.cuh; compile with -fmad=false like the library:
+// same order (detail/samplers.cuh; compile with -fmad=false like the library:
 // the reference is built without FMA contraction).  The state type holds the
 // four words of xoshiro256+ in registers; `state[i]` reads and writes them in
 // the reference's exported layout (hdr/prng.hpp:92-105), which is also the
@@ -37,15 +37,15 @@
 #pragma once
 #include <cstdio>
 
-#include "../../monty_b200/csrc/samplers.cuh"
-#include "../../monty_b200/csrc/density.cuh"
-#include "../../monty_b200/csrc/jump_constants.cuh"
+#include "detail/samplers.cuh"
+#include "detail/density.cuh"
+#include "detail/jump_constants.cuh"
 
 namespace monty {
 namespace random {
 
 namespace detail {
-#include "../../monty_b200/csrc/monty_tables.inc"
+#include "detail/monty_tables.inc"
 static __device__ const double f_zig_x[257] = { MONTY_ZIG_X_VALUES };
 static __device__ const double2 f_zig_xy[256] = { MONTY_ZIG_XY_VALUES };
 static __device__ const double f_tail_d[10] = { MONTY_TAIL_D_VALUES };
@@ -78,6 +78,16 @@ __device__ __forceinline__ void fail(const char* what) {
 #endif
 }
 }  // namespace detail
+
+// True when this translation unit really was compiled without FMA contraction
+// (the #error in detail/samplers.cuh only checks that the consumer SAID so):
+// a * b + c is evaluated on values for which the fused and the two-rounding
+// results differ.  Call it once from a test kernel of the consuming project.
+__device__ __forceinline__ bool contraction_is_off() {
+  volatile double a = 1.0 + 0x1p-30, b = 1.0 - 0x1p-30, c = -1.0;
+  const double x = a, y = b, z = c;
+  return x * y + z == 0.0;          // exact product is 1 - 2^-60: rounds to 1, fused gives -2^-60
+}
 
 // ---- generator state -------------------------------------------------------
 // hdr/xoshiro_state.hpp:20-39 + hdr/xoshiro256.hpp: four 64-bit words.
@@ -298,6 +308,17 @@ MONTY_B200_DENSITY(cauchy, dens_cauchy, Q2(location, scale), B2(location, scale)
 MONTY_B200_DENSITY(weibull, dens_weibull, Q2(shape, scale), B2(shape, scale))
 MONTY_B200_DENSITY(log_normal, dens_log_normal, Q2(mulog, sdlog), B2(mulog, sdlog))
 #undef MONTY_B200_DENSITY
+// inst/include/monty/random/density.hpp:355-409: zero-inflated count densities,
+// log(pi0 + (1 - pi0) f(0)) at x == 0 and log(1 - pi0) + log f(x) elsewhere
+template <typename T> __device__ __forceinline__ T zi_poisson(T x, T pi0, T lambda, bool log) {
+  return mb200::dens_zi_wrap<T>(x, pi0, mb200::dens_poisson<T>(x, lambda, true), log);
+}
+template <typename T> __device__ __forceinline__ T zi_negative_binomial_prob(T x, T pi0, T size, T prob, bool log) {
+  return mb200::dens_zi_wrap<T>(x, pi0, mb200::dens_negative_binomial_prob<T>(x, size, prob, true), log);
+}
+template <typename T> __device__ __forceinline__ T zi_negative_binomial_mu(T x, T pi0, T size, T mu, bool log) {
+  return mb200::dens_zi_wrap<T>(x, pi0, mb200::dens_negative_binomial_mu<T>(x, size, mu, true), log);
+}
 #undef Q1
 #undef Q2
 #undef Q3

@@ -37,15 +37,28 @@ def inline_multinomial(state, size, prob):
     return out
 
 
-MATH_FN = {"log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4}
+MATH_FN = {"log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4, "contraction_is_off": 5}
 
 
 def math_probe(fn, x):
-    """The samplers' own math routines (csrc/samplers.cuh) evaluated on the device."""
+    """The samplers' own math routines (include/monty_b200/detail/samplers.cuh) evaluated on the device."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.empty_like(x)
     check(lib.mb200_example_math_probe(C.c_int(MATH_FN[fn]), x.ctypes.data_as(C.c_void_p),
                                        y.ctypes.data_as(C.c_void_p), C.c_size_t(x.size)))
+    return y
+
+
+def zi_density(which, x, pi0, a, b=None, log=True):
+    """monty::density::zi_<which> evaluated through the device-side API."""
+    idx = {"poisson": 0, "negative_binomial_prob": 1, "negative_binomial_mu": 2}[which]
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, pi0, a)]
+    bb = np.ascontiguousarray(b, dtype=np.float64) if b is not None else None
+    y = np.empty_like(arrs[0])
+    check(lib.mb200_example_zi_density(C.c_int(idx), arrs[0].ctypes.data_as(C.c_void_p),
+                                       arrs[1].ctypes.data_as(C.c_void_p), arrs[2].ctypes.data_as(C.c_void_p),
+                                       bb.ctypes.data_as(C.c_void_p) if bb is not None else None,
+                                       C.c_int(1 if log else 0), y.ctypes.data_as(C.c_void_p), C.c_size_t(y.size)))
     return y
 
 

@@ -116,7 +116,15 @@ class MontyRngState:
         """Draw into a torch CUDA tensor `out` of shape (n_streams, n_samples)
         (float64, or float32 with real_type "f32").  `params` are torch CUDA
         float64 tensors of 1 or n_streams elements.  Asynchronous; call
-        `sync()` to wait and collect parameter errors."""
+        `sync()` to wait and collect parameter errors.
+
+        Ordering.  The launch runs on the handle's own (non-blocking) CUDA
+        stream.  It is ordered AFTER everything queued so far on torch's current
+        stream (so parameters produced by pending torch kernels are complete,
+        and a freshly allocated `out` is no longer in use by earlier work), and
+        torch's current stream is made to wait for it, so torch operations
+        issued afterwards on `out` see the draws.  The tensors are registered
+        with the caching allocator as in use on the handle's stream."""
         import torch
         d = DIST[dist] if isinstance(dist, str) else dist
         rt = real_type or self.real_type
@@ -140,8 +148,18 @@ class MontyRngState:
             ptrs[k] = p.data_ptr()
             lens[k] = p.numel()
         self._keepalive = (keep, out)
+        hs = torch.cuda.ExternalStream(self.cuda_stream(), device=out.device)
+        cur = torch.cuda.current_stream(out.device)
+        ordered = cur.cuda_stream != hs.cuda_stream
+        if ordered:
+            hs.wait_stream(cur)
         check(lib.mb200_rng_sample_dev(self.handle, d, 1 if rt == "f32" else 0, n_samples,
                                        ptrs, lens, C.c_void_p(out.data_ptr()), out_f32))
+        if ordered:
+            out.record_stream(hs)
+            for p in keep:
+                p.record_stream(hs)
+            cur.wait_stream(hs)
         return out
 
 

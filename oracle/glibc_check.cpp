@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY (see oracle/Makefile).
-// Host build of the PRODUCT's glibc-exact log / cos (monty_b200/csrc/glibc_math.cuh
+// Host build of the PRODUCT's glibc-exact log / cos (include/monty_b200/detail/glibc_math.cuh
 // compiled as plain C++ with g++ -mfma, every operation explicit) next to the
 // LIVE libm of the host it runs on -- the library the reference's std::log /
 // std::cos resolve to (hdr/normal_box_muller.hpp:27-34).  tests/test_glibc_math.py
@@ -9,7 +9,7 @@
 #include <cstdint>
 #include <cstring>
 
-#include "../monty_b200/csrc/glibc_math.cuh"
+#include "../include/monty_b200/detail/glibc_math.cuh"
 
 
 static inline uint64_t splitmix(uint64_t& s) {

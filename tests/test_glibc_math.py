@@ -1,4 +1,4 @@
-"""CPU check of the product's glibc-exact log / cos (monty_b200/csrc/glibc_math.cuh).
+"""CPU check of the product's glibc-exact log / cos (include/monty_b200/detail/glibc_math.cuh).
 
 The header compiles as plain host C++ (oracle/libglibc_check.so, g++ -mfma, no
 implicit contraction), so the SOURCE that runs on the device is compared here,
@@ -83,7 +83,7 @@ def test_tables_have_their_mathematical_meaning():
     sin / cos rows are double-doubles of sin / cos(k / 128) to 2^-100."""
     mp = pytest.importorskip("mpmath")
     mp.mp.prec = 200
-    txt = open(os.path.join(ROOT, "monty_b200", "csrc", "glibc_tables.inc")).read()
+    txt = open(os.path.join(ROOT, "include", "monty_b200", "detail", "glibc_tables.inc")).read()
 
     def macro(name):
         body = txt.split("#define %s " % name)[1]

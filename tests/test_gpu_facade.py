@@ -106,3 +106,30 @@ def test_sir_filter_estimates_a_likelihood(mb, ex):
         lls.append(ex.sir_filter(system, filt, SIR, TIMES, INCIDENCE))
     lls = np.array(lls)
     assert np.all(np.isfinite(lls)) and lls.std() < 1.0
+
+
+def test_zero_inflated_densities_of_the_device_api(mb, oracle):
+    """monty::density::zi_poisson / zi_negative_binomial_prob / _mu
+    (ref: inst/include/monty/random/density.hpp:355-409) through random.cuh,
+    against the bulk density kernels and the reference."""
+    from monty_b200 import examples
+    from cases import density_cases
+    n = 5000
+    for which, name in (("poisson", "zi_poisson"), ("negative_binomial_prob", "zi_negative_binomial_prob"),
+                        ("negative_binomial_mu", "zi_negative_binomial_mu")):
+        x, pars = density_cases(n)[name]
+        pars = [np.asarray(p, dtype=np.float64) for p in pars]
+        pars[0][:3] = [0.0, 1.0, 1.0]            # the pi0 == 0 and pi0 == 1 branches
+        for log in (True, False):
+            got = examples.zi_density(which, x.astype(np.float64), pars[0], pars[1], pars[2] if len(pars) > 2 else None, log)
+            bulk = mb.density._density(name, x, pars, log)
+            assert np.array_equal(got, bulk, equal_nan=True), name
+            exp = oracle.density(name, x, pars, log)
+            assert np.allclose(got, exp, rtol=1e-12, atol=1e-300, equal_nan=True), name
+
+
+def test_examples_library_is_built_without_fma_contraction():
+    """The device-side API's arithmetic contract (-fmad=false): checked at run
+    time by monty::random::contraction_is_off()."""
+    from monty_b200 import examples
+    assert examples.math_probe("contraction_is_off", np.zeros(4))[0] == 1.0

@@ -1,7 +1,7 @@
 """The samplers' own double-precision math routines evaluated ON THE DEVICE
 (through the examples library's probe kernel):
 
-  * m_log / m_log_normal and cos_0_2pi (csrc/glibc_math.cuh) must return the
+  * m_log / m_log_normal and cos_0_2pi (include/monty_b200/detail/glibc_math.cuh) must return the
     BITS of the host's libm -- glibc 2.39, what the reference's std::log /
     std::cos resolve to (hdr/normal_box_muller.hpp:27-34, hdr/exponential.hpp:26,
     hdr/gamma.hpp:36-50): with that Box-Muller normals, exponentials, gamma and

@@ -7,7 +7,7 @@ Bars (BASELINE.json north_star):
   * integer-valued draws (double): bit-exact up to a mismatch fraction <= 1e-6
     attributable to libm ulp differences -- we assert 0 mismatches here;
   * continuous draws (double): within 4 ulp.  The device's log and cos return
-    glibc's bits (csrc/glibc_math.cuh), so every sampler assembled from log,
+    glibc's bits (include/monty_b200/detail/glibc_math.cuh), so every sampler assembled from log,
     cos, sqrt and IEEE arithmetic alone -- exponential, the three normals,
     truncated normal, gamma with shape >= 1, beta with both shapes >= 1 -- is
     asserted BIT-IDENTICAL, shifted and scaled parameters included; the ones
@@ -435,3 +435,30 @@ def test_deterministic_errors(mb):
     assert np.array_equal(mb.monty_random_n_poisson(3, 2.5, rng), np.full((3, 2), 2.5))
     y = mb.monty_random_multinomial(10.0, np.array([0.2, 0.3, 0.5]), rng)
     assert np.allclose(y[:, 0], [2.0, 3.0, 5.0])
+
+
+def test_sample_dev_is_ordered_with_torchs_stream(mb):
+    """Parameters written by torch kernels that are still pending when
+    sample_dev is called, and a consumer on torch's stream right after it: the
+    handle's private stream must wait for the former and be waited for by the
+    latter (the launch used to race with both)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n, ns = 1 << 18, 8
+    a = mb.monty_rng_create(n, 11)
+    b = mb.monty_rng_create(n, 11)
+    lam_host = np.full(n, 7.5)
+    ref = np.asarray(mb.monty_random_n_poisson(ns, lam_host, a))          # host path: fully synchronous
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        lam = torch.zeros(n, dtype=torch.float64, device=dev)
+        big = torch.empty(1 << 27, dtype=torch.float64, device=dev)
+        for _ in range(20):
+            big.normal_()                      # keeps the stream busy ahead of the parameter write
+        lam.add_(7.5)                          # the parameter is only valid after this kernel
+        out = b.sample_dev("poisson", ns, [lam])
+        total = out.sum()                      # consumer on torch's stream, no explicit sync
+    got_sum = float(total.item())
+    b.sync()
+    assert np.array_equal(out.cpu().numpy(), ref.T)
+    assert got_sum == float(ref.sum())

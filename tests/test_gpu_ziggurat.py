@@ -7,7 +7,7 @@ expression inside it, and runs the tail out of line -- so the bar is
   * final generator states: bit-exact (every stream consumed exactly the
     reference's number of words);
   * draws: bit-exact in double, tail draws (|z| > x[1] = 3.65..., 3e-4 of
-    draws) included -- their log() returns glibc's bits (csrc/glibc_math.cuh);
+    draws) included -- their log() returns glibc's bits (include/monty_b200/detail/glibc_math.cuh);
     float real_type: tail draws go through logf and may differ by its ulps.
 Shapes cover ragged first/last windows (n_samples not a multiple of 32, odd
 n_samples -> scalar store path), n_streams not a multiple of 32, one warp-tile

@@ -1,4 +1,4 @@
-"""The lookup tables carried by the product (monty_b200/csrc/monty_tables.inc)
+"""The lookup tables carried by the product (include/monty_b200/detail/monty_tables.inc)
 and by the C oracle are DATA extracted from the reference
 (tools/extract_tables.py).  Check them against their mathematical definition
 (ref: scripts/update_ziggurat_tables, scripts/update_gamma_tables) and, when the
@@ -27,11 +27,11 @@ def parse_tables(path):
 
 @pytest.fixture(scope="module")
 def tables():
-    return parse_tables(os.path.join(ROOT, "monty_b200", "csrc", "monty_tables.inc"))
+    return parse_tables(os.path.join(ROOT, "include", "monty_b200", "detail", "monty_tables.inc"))
 
 
 def test_product_and_oracle_tables_identical():
-    a = open(os.path.join(ROOT, "monty_b200", "csrc", "monty_tables.inc")).read()
+    a = open(os.path.join(ROOT, "include", "monty_b200", "detail", "monty_tables.inc")).read()
     b = open(os.path.join(ROOT, "oracle", "oracle_tables.inc")).read()
     assert a == b
 

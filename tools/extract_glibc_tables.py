@@ -9,12 +9,12 @@ the same tables as glibc", not "an accurate log".  The algorithms are published
 (log: sysdeps/ieee754/dbl-64/e_log.c, Szabolcs Nagy's table-driven log from ARM
 optimized-routines; cos: sysdeps/ieee754/dbl-64/s_sin.c, the IBM Accurate
 Mathematical Library's do_sin / do_cos over __sincostab) and are restated in
-monty_b200/csrc/glibc_math.cuh (device) and oracle/glibc_math_port.c (CPU check);
+include/monty_b200/detail/glibc_math.cuh (device) and oracle/glibc_math_port.c (CPU check);
 the TABLES are data, read here from the image's own libm.so.6 (glibc 2.39,
 Ubuntu 2.39-0ubuntu8.5, the library the oracle links) and written as hex-float
 literals to
 
-    monty_b200/csrc/glibc_tables.inc
+    include/monty_b200/detail/glibc_tables.inc
 
 Tables:
     __log_data      ln2hi, ln2lo, poly[5], poly1[11], tab[128] {invc, logc}
@@ -174,4 +174,4 @@ if __name__ == "__main__":
         print("log_data at 0x%x, sincostab at 0x%x" % (r["log_addr"], r["sincos_addr"]))
         print("missing scalar constants:", r["missing"])
     else:
-        main(os.path.join(ROOT, "monty_b200", "csrc", "glibc_tables.inc"))
+        main(os.path.join(ROOT, "include", "monty_b200", "detail", "glibc_tables.inc"))
