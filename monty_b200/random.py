@@ -123,8 +123,7 @@ class MontyRngState:
         stream (so parameters produced by pending torch kernels are complete,
         and a freshly allocated `out` is no longer in use by earlier work), and
         torch's current stream is made to wait for it, so torch operations
-        issued afterwards on `out` see the draws.  The tensors are registered
-        with the caching allocator as in use on the handle's stream."""
+        issued afterwards on `out` see the draws."""
         import torch
         d = DIST[dist] if isinstance(dist, str) else dist
         rt = real_type or self.real_type
@@ -156,9 +155,9 @@ class MontyRngState:
         check(lib.mb200_rng_sample_dev(self.handle, d, 1 if rt == "f32" else 0, n_samples,
                                        ptrs, lens, C.c_void_p(out.data_ptr()), out_f32))
         if ordered:
-            out.record_stream(hs)
-            for p in keep:
-                p.record_stream(hs)
+            # torch's stream now waits for the draws, so stream order also protects the
+            # tensors' memory: the caching allocator reuses a freed block on the stream it
+            # was allocated on, i.e. after this wait
             cur.wait_stream(hs)
         return out
 
