@@ -7,12 +7,14 @@
 // the routine it replaces.  There is no CPU fallback anywhere in this file:
 // every sample is produced by a CUDA kernel or the call fails.
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -56,6 +58,10 @@ struct mb200_rng {
   size_t par_cap[MB200_MAX_PARAMS] = {0, 0, 0, 0};
   void* d_out = nullptr;
   size_t out_cap = 0;
+  // pinned staging ring for transfers to / from PAGEABLE host vectors (what R
+  // hands us), allocated on first use: see copy_to_host / copy_from_host
+  char* stage[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
   std::string last_error;
   // deferred error context of the last device-resident sample call
   bool pending = false;
@@ -90,6 +96,163 @@ int ensure(mb200_rng* rng, void** p, size_t* cap, size_t bytes) {
   if (*p) { CU(cudaStreamSynchronize(rng->stream)); CU(cudaFree(*p)); *p = nullptr; *cap = 0; }
   CU(cudaMalloc(p, bytes));
   *cap = bytes;
+  return MB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Transfers between device memory and PAGEABLE host memory.
+//
+// R's vectors (the parameters it passes, the cpp11::writable::doubles the
+// result lands in) are ordinary malloc'ed memory.  cudaMemcpy on such memory
+// goes through the driver's internal staging buffer with a single-threaded
+// host copy: 10-25 GB/s, and the call blocks.  Here large transfers are cut
+// into 32 MB chunks that travel by DMA between the device and a ring of three
+// pinned staging buffers (full PCIe rate, asynchronous), while a small pool of
+// host threads copies the previous chunk between the ring and the caller's
+// vector -- the two overlap, and the host side runs at several threads' memory
+// bandwidth.  Pinned callers (the bench's e2e leg, anything cudaHostRegister'ed)
+// and small transfers keep the plain asynchronous copy.
+// ---------------------------------------------------------------------------
+constexpr size_t kStageChunk = 32u << 20;
+constexpr size_t kStageMin = 8u << 20;        // below this one plain copy is cheaper
+
+class CopyPool {
+ public:
+  // never destroyed: its (detached) workers outlive static destruction
+  static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }
+  // memcpy(dst, src, n) split over the pool's threads; returns when done
+  void copy(char* dst, const char* src, size_t n) {
+    const size_t nt = workers_.size();
+    if (nt == 0 || n < (4u << 20)) { std::memcpy(dst, src, n); return; }
+    std::unique_lock<std::mutex> lock(m_);
+    dst_ = dst; src_ = src; n_ = n; pending_ = nt; ++generation_;
+    cv_.notify_all();
+    done_.wait(lock, [&] { return pending_ == 0; });
+  }
+ private:
+  CopyPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 0);
+    for (unsigned t = 0; t < nt; ++t) workers_.emplace_back([this, t, nt] { run(t, nt); });
+    for (auto& w : workers_) w.detach();
+  }
+  void run(unsigned t, unsigned nt) {
+    unsigned long long seen = 0;
+    for (;;) {
+      char* d; const char* s; size_t n;
+      {
+        std::unique_lock<std::mutex> lock(m_);
+        cv_.wait(lock, [&] { return generation_ != seen; });
+        seen = generation_; d = dst_; s = src_; n = n_;
+      }
+      const size_t per = ((n / nt) + 4095) & ~static_cast<size_t>(4095);
+      const size_t lo = per * t < n ? per * t : n, hi = per * (t + 1) < n ? per * (t + 1) : n;
+      if (t == nt - 1 && hi < n) std::memcpy(d + hi, s + hi, n - hi);
+      if (hi > lo) std::memcpy(d + lo, s + lo, hi - lo);
+      {
+        std::lock_guard<std::mutex> lock(m_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  char* dst_ = nullptr; const char* src_ = nullptr; size_t n_ = 0, pending_ = 0;
+  unsigned long long generation_ = 0;
+};
+
+bool host_is_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_stage(mb200_rng* rng) {
+  for (int s = 0; s < 3; ++s) {
+    if (!rng->stage[s]) CU(cudaMallocHost(&rng->stage[s], kStageChunk));
+    if (!rng->stage_ev[s]) CU(cudaEventCreateWithFlags(&rng->stage_ev[s], cudaEventDisableTiming));
+  }
+  return MB200_OK;
+}
+
+// device -> host vector, ordered on the handle's stream.  Large pageable
+// destinations are complete on return; otherwise the copy is queued and the
+// caller's next synchronisation (fetch_err) completes it.
+int copy_to_host(mb200_rng* rng, void* dst_host, const void* src_dev, size_t bytes) {
+  if (bytes < kStageMin || !host_is_pageable(dst_host)) {
+    CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, rng->stream));
+    return MB200_OK;
+  }
+  int rc = ensure_stage(rng);
+  if (rc != MB200_OK) return rc;
+  const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+  auto len = [&](size_t i) { return i + 1 < n_chunks ? kStageChunk : bytes - i * kStageChunk; };
+  auto issue = [&](size_t i) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(rng->stage[i % 3], static_cast<const char*>(src_dev) + i * kStageChunk, len(i),
+                                    cudaMemcpyDeviceToHost, rng->stream);
+    return e == cudaSuccess ? cudaEventRecord(rng->stage_ev[i % 3], rng->stream) : e;
+  };
+  for (size_t i = 0; i < n_chunks && i < 3; ++i) CU(issue(i));
+  for (size_t i = 0; i < n_chunks; ++i) {
+    CU(cudaEventSynchronize(rng->stage_ev[i % 3]));
+    CopyPool::get().copy(static_cast<char*>(dst_host) + i * kStageChunk, rng->stage[i % 3], len(i));
+    if (i + 3 < n_chunks) CU(issue(i + 3));
+  }
+  return MB200_OK;
+}
+
+// host vector -> device, ordered on the handle's stream (the source may be
+// reused as soon as the call returns only in the staged case; the plain
+// asynchronous copy of a pageable source is staged by the driver before it returns)
+int copy_from_host(mb200_rng* rng, void* dst_dev, const void* src_host, size_t bytes) {
+  if (bytes < kStageMin || !host_is_pageable(src_host)) {
+    CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, rng->stream));
+    return MB200_OK;
+  }
+  int rc = ensure_stage(rng);
+  if (rc != MB200_OK) return rc;
+  const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+  for (size_t i = 0; i < n_chunks; ++i) {
+    const size_t n = i + 1 < n_chunks ? kStageChunk : bytes - i * kStageChunk;
+    CU(cudaEventSynchronize(rng->stage_ev[i % 3]));        // the slot's previous DMA (this or an earlier call) has read it
+    CopyPool::get().copy(rng->stage[i % 3], static_cast<const char*>(src_host) + i * kStageChunk, n);
+    CU(cudaMemcpyAsync(static_cast<char*>(dst_dev) + i * kStageChunk, rng->stage[i % 3], n, cudaMemcpyHostToDevice,
+                       rng->stream));
+    CU(cudaEventRecord(rng->stage_ev[i % 3], rng->stream));
+  }
+  return MB200_OK;
+}
+
+// Per-device scratch of the host-buffer density call (mb200_density).
+struct DensityScratch {
+  std::mutex m;
+  mb200_rng* io = nullptr;       // stream + staging ring (no generator state)
+  void* x = nullptr; size_t x_cap = 0;
+  void* p[MB200_MAX_PARAMS] = {nullptr, nullptr, nullptr, nullptr};
+  size_t p_cap[MB200_MAX_PARAMS] = {0, 0, 0, 0};
+  void* out = nullptr; size_t out_cap = 0;
+  double* sum = nullptr;
+  double* h_sum = nullptr;       // pinned
+};
+DensityScratch* g_density_scratch[64];
+std::mutex g_density_scratch_mutex;
+
+int density_scratch(int device, DensityScratch** out) {
+  mb200_rng* rng = nullptr;
+  if (device < 0 || device >= 64) return fail(MB200_ERR_ARG, nullptr, "device ordinal %d out of range", device);
+  std::lock_guard<std::mutex> lock(g_density_scratch_mutex);
+  if (!g_density_scratch[device]) {
+    std::unique_ptr<DensityScratch> sc(new DensityScratch());
+    std::unique_ptr<mb200_rng> io(new mb200_rng());
+    io->device = device;
+    CU(cudaStreamCreateWithFlags(&io->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&sc->sum, sizeof(double)));
+    CU(cudaMallocHost(&sc->h_sum, sizeof(double)));
+    sc->io = io.release();
+    g_density_scratch[device] = sc.release();
+  }
+  *out = g_density_scratch[device];
   return MB200_OK;
 }
 
@@ -347,6 +510,10 @@ void mb200_rng_free(mb200_rng* rng) {
   if (rng->h_err) cudaFreeHost(rng->h_err);
   for (int k = 0; k < MB200_MAX_PARAMS; ++k) cudaFree(rng->d_par[k]);
   cudaFree(rng->d_out);
+  for (int s = 0; s < 3; ++s) {
+    if (rng->stage[s]) cudaFreeHost(rng->stage[s]);
+    if (rng->stage_ev[s]) cudaEventDestroy(rng->stage_ev[s]);
+  }
   if (rng->stream) cudaStreamDestroy(rng->stream);
   delete rng;
 }
@@ -482,7 +649,8 @@ int mb200_rng_sample(mb200_rng* rng, int dist, int real_type, size_t n_samples,
     const size_t bytes = param_len[k] * sizeof(double);
     rc = ensure(rng, reinterpret_cast<void**>(&rng->d_par[k]), &rng->par_cap[k], bytes);
     if (rc != MB200_OK) return rc;
-    CU(cudaMemcpyAsync(rng->d_par[k], params_host[k], bytes, cudaMemcpyHostToDevice, rng->stream));
+    rc = copy_from_host(rng, rng->d_par[k], params_host[k], bytes);
+    if (rc != MB200_OK) return rc;
     a.par[k] = rng->d_par[k];
     a.pstride[k] = param_len[k] == 1 ? 0u : 1u;
     all_scalar = all_scalar && param_len[k] == 1;
@@ -520,7 +688,8 @@ int mb200_rng_sample(mb200_rng* rng, int dist, int real_type, size_t n_samples,
     a.n_streams = n_active;
     a.n_samples = n_samples;
     CU(launch_sample(dist, real_type, 0, false, a, rng->sm_count, rng->stream));
-    CU(cudaMemcpyAsync(out_host, rng->d_out, out_bytes, cudaMemcpyDeviceToHost, rng->stream));
+    rc = copy_to_host(rng, out_host, rng->d_out, out_bytes);
+    if (rc != MB200_OK) return rc;
     rc = fetch_err(rng);
     if (rc != MB200_OK) return rc;
     if (rng->h_err->stream != ~0ull && rng->h_err->stream < n_active) {
@@ -709,33 +878,38 @@ int mb200_density(int dens, int real_type, size_t n,
   CU(cudaSetDevice(device));
   CU(ensure_lgamma_table(device, nullptr));
   if (n == 0) { if (sum_out) *sum_out = 0.0; return MB200_OK; }
-  void* d_x = nullptr;
-  void* d_p[MB200_MAX_PARAMS] = {nullptr, nullptr, nullptr, nullptr};
-  double* d_out = nullptr;
-  double* d_sum = nullptr;
-  int rc = MB200_OK;
-  cudaError_t e = cudaSuccess;
-  auto upload = [&](void** dst, const void* src, int is_i32) {
-    const size_t bytes = n * (is_i32 ? sizeof(int32_t) : sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(dst, bytes);
-    if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
-  };
-  upload(&d_x, x_host, x_is_i32);
-  for (int k = 0; k < np; ++k) upload(&d_p[k], params_host[k], param_is_i32 ? param_is_i32[k] : 0);
-  if (e == cudaSuccess && out_host) e = cudaMalloc(&d_out, n * sizeof(double));
-  if (e == cudaSuccess && sum_out) e = cudaMalloc(&d_sum, sizeof(double));
-  if (e == cudaSuccess) {
-    rc = mb200_density_dev(dens, real_type, n, d_x, x_is_i32, d_p, param_is_i32, log,
-                           d_out, d_sum, device, nullptr);
-    if (rc == MB200_OK && out_host) e = cudaMemcpy(out_host, d_out, n * sizeof(double), cudaMemcpyDeviceToHost);
-    if (rc == MB200_OK && e == cudaSuccess && sum_out) e = cudaMemcpy(sum_out, d_sum, sizeof(double), cudaMemcpyDeviceToHost);
-  }
-  cudaFree(d_x);
-  for (int k = 0; k < MB200_MAX_PARAMS; ++k) cudaFree(d_p[k]);
-  cudaFree(d_out);
-  cudaFree(d_sum);
+  // Device buffers, stream and pinned staging ring are kept per device and grow
+  // on demand (a likelihood evaluated in an MCMC loop calls this thousands of
+  // times with the same lengths: no cudaMalloc / cudaFree per call); the calls of
+  // one device are serialised by the scratch's mutex.
+  DensityScratch* sc = nullptr;
+  int rc = density_scratch(device, &sc);
   if (rc != MB200_OK) return rc;
-  CU(e);
+  std::lock_guard<std::mutex> lock(sc->m);
+  rng = sc->io;                               // transfers and error text go through this pseudo-handle
+  void* d_p[MB200_MAX_PARAMS] = {nullptr, nullptr, nullptr, nullptr};
+  const size_t xb = n * (x_is_i32 ? sizeof(int32_t) : sizeof(double));
+  rc = ensure(rng, &sc->x, &sc->x_cap, xb);
+  if (rc == MB200_OK) rc = copy_from_host(rng, sc->x, x_host, xb);
+  for (int k = 0; k < np && rc == MB200_OK; ++k) {
+    const size_t pb = n * ((param_is_i32 && param_is_i32[k]) ? sizeof(int32_t) : sizeof(double));
+    rc = ensure(rng, &sc->p[k], &sc->p_cap[k], pb);
+    if (rc == MB200_OK) rc = copy_from_host(rng, sc->p[k], params_host[k], pb);
+    d_p[k] = sc->p[k];
+  }
+  if (rc == MB200_OK && out_host) rc = ensure(rng, &sc->out, &sc->out_cap, n * sizeof(double));
+  if (rc != MB200_OK) return rc;
+  rc = mb200_density_dev(dens, real_type, n, sc->x, x_is_i32, d_p, param_is_i32, log,
+                         out_host ? static_cast<double*>(sc->out) : nullptr, sum_out ? sc->sum : nullptr, device,
+                         rng->stream);
+  if (rc != MB200_OK) return rc;
+  if (out_host) {
+    rc = copy_to_host(rng, out_host, sc->out, n * sizeof(double));
+    if (rc != MB200_OK) return rc;
+  }
+  if (sum_out) CU(cudaMemcpyAsync(sc->h_sum, sc->sum, sizeof(double), cudaMemcpyDeviceToHost, rng->stream));
+  CU(cudaStreamSynchronize(rng->stream));
+  if (sum_out) *sum_out = *sc->h_sum;
   return MB200_OK;
 }
 

@@ -458,7 +458,7 @@ def test_sample_dev_is_ordered_with_torchs_stream(mb):
         lam.add_(7.5)                          # the parameter is only valid after this kernel
         out = b.sample_dev("poisson", ns, [lam])
         total = out.sum()                      # consumer on torch's stream, no explicit sync
-    got_sum = float(total.item())
+        got_sum = float(total.item())          # (.item() waits for the stream it is issued on)
     b.sync()
     assert np.array_equal(out.cpu().numpy(), ref.T)
     assert got_sum == float(ref.sum())
