@@ -214,6 +214,17 @@ int mb200_rng_sync(mb200_rng* rng);
  * before the first offending stream are advanced, the offender and later
  * streams are untouched, and the call fails with MB200_ERR_PARAM and the
  * reference's message text.
+ * One documented divergence: a DATA-DEPENDENT failure inside a composition
+ * (negative_binomial -> Poisson on the gamma draw, beta_binomial -> binomial on
+ * the beta draw, multinomial's inner binomials: errors that depend on what was
+ * drawn, not on the parameters) is detected after the launch.  The message is
+ * the reference's, for the smallest failing stream, but by then every valid
+ * stream of the call has advanced through all its draws, including streams
+ * after the failing one, and the failing stream's output is NaN from the
+ * failure on; the reference stops at the failing draw and leaves later streams
+ * untouched (src/random.cpp:211-228).  These failures need parameters at the
+ * edge of the double range (a gamma draw that overflows); the parity tests
+ * cover the message text, not the state of the later streams.
  */
 int mb200_rng_sample(mb200_rng* rng, int dist, int real_type, size_t n_samples,
                      const double* const* params_host, const size_t* param_len,

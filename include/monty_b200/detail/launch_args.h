@@ -27,6 +27,8 @@ struct ErrRec {
   int code;                    // SampleError
   unsigned work;               // tile counter of the self-scheduling kernels (starts at ~0u)
   double vals[3];              // values for data-dependent messages
+  unsigned lock;               // ~0u: free (the record is reset with a 0xFF fill); guards code / vals / owner
+  unsigned pad;
 };
 
 struct SampleArgs {

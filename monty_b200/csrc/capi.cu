@@ -83,6 +83,14 @@ int fail(int code, mb200_rng* rng, const char* fmt, ...) {
   return code;
 }
 
+// Entry points switch to the handle's device; the caller's current device is
+// restored on return (mb200_*_dev are called from inside torch processes).
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 #define CU(call)                                                                   \
   do {                                                                             \
     cudaError_t e__ = (call);                                                      \
@@ -266,7 +274,13 @@ struct LgammaTable { double* d = nullptr; float* f = nullptr; bool ready = false
 // its memory back) and up to kPartialSlots calls can be in flight per device.
 constexpr int kPartialSlots = 64;
 constexpr int kPartialSlotDoubles = 2048;     // >= density_grid(): 8 blocks per SM
-struct PartialRing { double* base = nullptr; std::atomic<unsigned> next{0}; };
+struct PartialRing {
+  double* base = nullptr;
+  std::atomic<unsigned> next{0};
+  // recorded after the reduction that reads a slot; the next user of the slot --
+  // possibly on another stream -- waits for it before its kernel writes there
+  cudaEvent_t used[kPartialSlots] = {};
+};
 PartialRing g_partials[64];
 LgammaTable g_lgamma_table[64];
 std::mutex g_lgamma_mutex;
@@ -287,6 +301,10 @@ cudaError_t ensure_lgamma_table(int device, cudaStream_t st) {
     e = cudaMalloc(&g_partials[device].base, sizeof(double) * kPartialSlots * kPartialSlotDoubles);
   }
   t.ready = e == cudaSuccess;
+  if (!t.ready) {                      // nothing half-built survives a failure: the next call starts over
+    cudaFree(t.d); cudaFree(t.f); cudaFree(g_partials[device].base);
+    t.d = nullptr; t.f = nullptr; g_partials[device].base = nullptr;
+  }
   return e;
 }
 
@@ -431,8 +449,10 @@ int mb200_rng_create(uint64_t seed, const uint8_t* seed_state_host, size_t seed_
   try { alg = &algebra(); } catch (const std::exception& e) {
     return fail(MB200_ERR_STATE, nullptr, "%s", e.what());
   }
+  DeviceGuard device_guard;
   CU(cudaSetDevice(device));
-  std::unique_ptr<mb200_rng> h(new mb200_rng());
+  // mb200_rng_free releases whatever has been allocated when a step below fails
+  std::unique_ptr<mb200_rng, void (*)(mb200_rng*)> h(new mb200_rng(), mb200_rng_free);
   rng = h.get();
   rng->device = device;
   rng->n_streams = n_streams;
@@ -503,6 +523,7 @@ int mb200_rng_create(uint64_t seed, const uint8_t* seed_state_host, size_t seed_
 
 void mb200_rng_free(mb200_rng* rng) {
   if (!rng) return;
+  DeviceGuard device_guard;
   cudaSetDevice(rng->device);
   if (rng->stream) cudaStreamSynchronize(rng->stream);
   cudaFree(rng->d_state);
@@ -531,6 +552,7 @@ int mb200_rng_state(mb200_rng* rng, uint8_t* out_host, size_t len) {
     return fail(MB200_ERR_STATE, rng, "state buffer must hold %d bytes (but was %d)",
                 (int)(rng->n_streams * 32), (int)len);
   }
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   CU(cudaMemcpyAsync(out_host, rng->d_state, len, cudaMemcpyDeviceToHost, rng->stream));
   CU(cudaStreamSynchronize(rng->stream));
@@ -544,6 +566,7 @@ int mb200_rng_set_state(mb200_rng* rng, const uint8_t* value_host, size_t len) {
     return fail(MB200_ERR_STATE, rng, "'value' must be a raw vector of length %d (but was %d)",
                 (int)(rng->n_streams * 32), (int)len);
   }
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   CU(cudaMemcpyAsync(rng->d_state, value_host, len, cudaMemcpyHostToDevice, rng->stream));
   CU(cudaStreamSynchronize(rng->stream));
@@ -554,6 +577,7 @@ static int jump_all(mb200_rng* rng, int n, bool is_long) {
   if (!rng) return fail(MB200_ERR_ARG, rng, "NULL argument");
   if (n < 0) return fail(MB200_ERR_ARG, rng, "'n' must be non-negative");
   if (n == 0) return MB200_OK;
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   const Poly256 p = is_long ? algebra().long_jumps(n) : algebra().jumps(n);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -565,6 +589,7 @@ int mb200_rng_long_jump(mb200_rng* rng, int n) { return jump_all(rng, n, true); 
 
 int mb200_rng_sync(mb200_rng* rng) {
   if (!rng) return fail(MB200_ERR_ARG, rng, "NULL argument");
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   if (!rng->pending) { CU(cudaStreamSynchronize(rng->stream)); return MB200_OK; }
   rng->pending = false;
@@ -601,6 +626,7 @@ int mb200_rng_sample_dev(mb200_rng* rng, int dist, int real_type, size_t n_sampl
   if (!out_dev) return fail(MB200_ERR_ARG, rng, "out_dev must not be NULL");
   int rc = check_param_lengths(rng, dist, param_len);
   if (rc != MB200_OK) return rc;
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   if (rng->pending) { rc = mb200_rng_sync(rng); if (rc != MB200_OK) return rc; }
   SampleArgs a{};
@@ -637,6 +663,7 @@ int mb200_rng_sample(mb200_rng* rng, int dist, int real_type, size_t n_samples,
   if (rc != MB200_OK) return rc;
   if (n_samples == 0) return MB200_OK;
   if (!out_host) return fail(MB200_ERR_ARG, rng, "out_host must not be NULL");
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   if (rng->pending) { rc = mb200_rng_sync(rng); if (rc != MB200_OK) return rc; }
   if (rng->deterministic) return sample_deterministic(rng, dist, real_type, n_samples, params_host, param_len, out_host);
@@ -725,6 +752,7 @@ int mb200_rng_multinomial(mb200_rng* rng, size_t n_samples,
                 (int)rng->n_streams, (int)prob_cols);
   }
   if (n_samples == 0 || prob_len == 0) return MB200_OK;
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   int rc;
   if (rng->pending) { rc = mb200_rng_sync(rng); if (rc != MB200_OK) return rc; }
@@ -770,6 +798,7 @@ int mb200_rng_raw(mb200_rng* rng, int gen, size_t n_samples, uint64_t* out_host)
     return fail(MB200_ERR_ARG, rng, "raw: generator must be a xoshiro256 variant");
   }
   if (n_samples == 0) return MB200_OK;
+  DeviceGuard device_guard;
   CU(cudaSetDevice(rng->device));
   const size_t bytes = rng->n_streams * n_samples * sizeof(uint64_t);
   int rc = ensure(rng, &rng->d_out, &rng->out_cap, bytes);
@@ -791,6 +820,7 @@ int mb200_xoshiro_run(int gen, uint64_t seed, int n, int device,
   if (mb200_device_count() <= device || device < 0) {
     return fail(MB200_ERR_CUDA, nullptr, "no usable CUDA device %d (monty_b200 has no CPU fallback)", device);
   }
+  DeviceGuard device_guard;
   CU(cudaSetDevice(device));
   uint64_t* d = nullptr;
   CU(cudaMalloc(&d, (3 * n + 8) * sizeof(uint64_t)));
@@ -822,6 +852,7 @@ int mb200_density_dev(int dens, int real_type, size_t n,
   if (real_type != MB200_REAL_F64 && real_type != MB200_REAL_F32) {
     return fail(MB200_ERR_ARG, nullptr, "unknown real_type %d", real_type);
   }
+  DeviceGuard device_guard;
   CU(cudaSetDevice(device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   CU(ensure_lgamma_table(device, st));
@@ -845,11 +876,17 @@ int mb200_density_dev(int dens, int real_type, size_t n,
   int grid = density_max_partials(sm);
   double* partial = nullptr;
   bool pooled = false;
+  unsigned slot = 0;
   if (sum_dev) {
     if (device < 64 && g_partials[device].base && grid <= kPartialSlotDoubles) {
-      const unsigned slot = g_partials[device].next.fetch_add(1, std::memory_order_relaxed) % kPartialSlots;
+      slot = g_partials[device].next.fetch_add(1, std::memory_order_relaxed) % kPartialSlots;
       partial = g_partials[device].base + static_cast<size_t>(slot) * kPartialSlotDoubles;
       pooled = true;
+      if (!g_partials[device].used[slot]) {
+        CU(cudaEventCreateWithFlags(&g_partials[device].used[slot], cudaEventDisableTiming));
+      } else {
+        CU(cudaStreamWaitEvent(st, g_partials[device].used[slot], 0));
+      }
     } else {
       CU(cudaMallocAsync(&partial, grid * sizeof(double), st));
     }
@@ -860,7 +897,8 @@ int mb200_density_dev(int dens, int real_type, size_t n,
   if (sum_dev) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CU(launch_reduce_partials(partial, grid, sum_dev, st));
-    if (!pooled) CU(cudaFreeAsync(partial, st));
+    if (pooled) CU(cudaEventRecord(g_partials[device].used[slot], st));
+    else CU(cudaFreeAsync(partial, st));
   }
   return MB200_OK;
 }
@@ -875,6 +913,7 @@ int mb200_density(int dens, int real_type, size_t n,
   if (mb200_device_count() <= device || device < 0) {
     return fail(MB200_ERR_CUDA, nullptr, "no usable CUDA device %d (monty_b200 has no CPU fallback)", device);
   }
+  DeviceGuard device_guard;
   CU(cudaSetDevice(device));
   CU(ensure_lgamma_table(device, nullptr));
   if (n == 0) { if (sum_out) *sum_out = 0.0; return MB200_OK; }

@@ -66,10 +66,23 @@ __device__ __forceinline__ void report_error(ErrRec* err, unsigned long long str
                                              const double* vals) {
   const unsigned long long old = atomicMin(&err->stream, stream);
   if (stream < old) {
-    err->code = code;
-    if (vals) { err->vals[0] = vals[0]; err->vals[1] = vals[1]; err->vals[2] = vals[2]; }
-    __threadfence();
-    err->owner = stream;
+    // The smallest stream wins the index atomically; its code and values must
+    // describe the SAME stream, so they are written under a lock and only by a
+    // thread that still is the minimum (two failing streams used to be able to
+    // leave one's index with the other's values).  Error path only.
+    bool done = false;
+    while (!done) {
+      if (atomicCAS(&err->lock, ~0u, 0u) == ~0u) {
+        if (*reinterpret_cast<volatile unsigned long long*>(&err->stream) == stream) {
+          err->code = code;
+          if (vals) { err->vals[0] = vals[0]; err->vals[1] = vals[1]; err->vals[2] = vals[2]; }
+          err->owner = stream;
+        }
+        __threadfence();
+        atomicExch(&err->lock, ~0u);
+        done = true;
+      }
+    }
   }
 }
 
