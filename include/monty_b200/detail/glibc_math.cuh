@@ -389,7 +389,9 @@ GM_FN double cos_medium_lockstep(double x) {
   double r = sincos_core(a, da, is_sin);
   if (is_sin && f_abs(a) < GLIBC_SC_SIN_TAYLOR_LIMIT) r = taylor_sin(a, da);
   if (neg) r = f_neg(r);
-  return k < 0x3e400000u ? 1.0 : r;
+  // |x| < 2^-27 (s_sin.c returns 1.0 outright): do_cos gives the same bits, its
+  // correction term is below 2^-55, so no test is needed here
+  return r;
 }
 
 }  // namespace glibc
