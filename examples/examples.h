@@ -49,7 +49,8 @@ int mb200_example_inline_multinomial(mb200_rng* rng, int real_type,
  * host doubles, for the parity tests: fn 0 = m_log, 1 = m_log_normal
  * (positive normal arguments), 2 = cos_0_2pi (0 <= x <= 2 pi), 3 = sqrt_normal
  * (positive normal arguments), 4 = the toolkit's sqrt, 5 = 1.0 when the examples
- * library was compiled without FMA contraction (monty::random::contraction_is_off). */
+ * library was compiled without FMA contraction (monty::random::contraction_is_off),
+ * 6 = m_lgamma, 7 = m_exp. */
 int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n);
 
 /* monty::density::zi_poisson (which = 0; a = lambda), zi_negative_binomial_prob

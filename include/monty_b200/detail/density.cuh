@@ -57,8 +57,16 @@ template <typename T> __device__ T dens_negative_binomial_mu(T x, T size, T mu, 
       ret = x * log_prob - mu - m_lgamma(x + 1) + m_log1p(x * (x - 1) / (2 * size));
     } else {
       const T prob = size / (size + mu);
-      ret = m_lgamma(x + size) - m_lgamma(size) - m_lgamma(x + 1) +
-        size * m_log(prob) + x * m_log(1 - prob);
+      if constexpr (sizeof(T) == 8) {
+        // the two non-integer lgammas as one batch (same bits as two calls)
+        const double arg[2] = {x + size, size};
+        double lgv[2];
+        m_lgamma_batch<2>(arg, lgv);
+        ret = lgv[0] - lgv[1] - m_lgamma(x + 1) + size * m_log(prob) + x * m_log(1 - prob);
+      } else {
+        ret = m_lgamma(x + size) - m_lgamma(size) - m_lgamma(x + 1) +
+          size * m_log(prob) + x * m_log(1 - prob);
+      }
     }
   }
   return maybe_log(ret, lg);
@@ -73,6 +81,15 @@ template <typename T> __device__ T dens_beta_binomial_ab(T x, T size, T a, T b, 
   T ret;
   if (x == 0 && size == 0) ret = 0;
   else if (x > size) ret = -Lim<T>::inf();
+  else if constexpr (sizeof(T) == 8) {
+    // lbeta(p, q) - lbeta(a, b) = six lgammas of non-integer arguments: one batch
+    // (same bits, same order of the sums as d_lbeta: lgamma(x) + lgamma(y) - lgamma(x + y))
+    const double p = x + a, q = size - x + b;
+    const double arg[6] = {p, q, p + q, a, b, a + b};
+    double lgv[6];
+    m_lgamma_batch<6>(arg, lgv);
+    ret = d_lchoose<T>(size, x) + (lgv[0] + lgv[1] - lgv[2]) - (lgv[3] + lgv[4] - lgv[5]);
+  }
   else ret = d_lchoose<T>(size, x) + d_lbeta<T>(x + a, size - x + b) - d_lbeta<T>(a, b);
   return maybe_log(ret, lg);
 }
@@ -138,7 +155,7 @@ template <typename T> __device__ T dens_truncated_normal(T x, T mu, T sd, T min,
     const double z_min = 0.5 * erfc(-y_min / 1.41421356237309504880);
     const double z_max = 0.5 * erfc(-y_max / 1.41421356237309504880);
     const double z = z_max - z_min;
-    ret = d - log(z);
+    ret = d - m_log(z);
   }
   return maybe_log(ret, lg);
 }
@@ -147,8 +164,8 @@ template <typename T> __device__ T dens_cauchy(T x, T location, T scale, bool lg
   // maybe_log<double> is what gets deduced
   const T q = (x - location) / scale;
   const T q2 = sizeof(T) == 4 ? static_cast<T>(pow(static_cast<double>(q), 2.0)) : static_cast<T>(pow(q, 2.0));
-  const double ret = -log(M_PI) - m_log(scale) - m_log1p(q2);
-  return lg ? static_cast<T>(ret) : static_cast<T>(exp(ret));
+  const double ret = -m_log(M_PI) - m_log(scale) - m_log1p(q2);
+  return lg ? static_cast<T>(ret) : static_cast<T>(m_exp(ret));
 }
 template <typename T> __device__ T dens_weibull(T x, T shape, T scale, bool lg) {   // :326-340
   T ret;

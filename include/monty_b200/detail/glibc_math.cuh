@@ -54,6 +54,7 @@ struct alignas(32) SinCosRow2 { double P, p, Q, q; };    // lock-step rows, see 
 static __device__ const LogRow g_log_tab[128] = GLIBC_LOG_TAB;
 static __device__ __align__(32) const double g_sincos_tab[440] = GLIBC_SINCOS_TAB;
 static __device__ const SinCosRow2 g_sincos_rows[220] = GLIBC_SINCOS_ROWS;
+static __device__ __align__(16) const unsigned long long g_exp_tab[256] = GLIBC_EXP_TAB;
 static __constant__ double c_log_poly[5] = GLIBC_LOG_POLY;
 static __constant__ double c_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
@@ -61,6 +62,7 @@ static __constant__ double c_log_poly1[11] = GLIBC_LOG_POLY1;
 static const LogRow h_log_tab[128] = GLIBC_LOG_TAB;
 static const double h_sincos_tab[440] = GLIBC_SINCOS_TAB;
 static const SinCosRow2 h_sincos_rows[220] = GLIBC_SINCOS_ROWS;
+static const unsigned long long h_exp_tab[256] = GLIBC_EXP_TAB;
 static const double h_log_poly[5] = GLIBC_LOG_POLY;
 static const double h_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
@@ -71,6 +73,7 @@ GM_FN double f_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 GM_FN double f_add(double a, double b) { return __dadd_rn(a, b); }
 GM_FN double f_sub(double a, double b) { return __dadd_rn(a, -b); }
 GM_FN double f_mul(double a, double b) { return __dmul_rn(a, b); }
+GM_FN double f_div(double a, double b) { return __ddiv_rn(a, b); }
 GM_FN uint64_t f_bits(double x) { return static_cast<uint64_t>(__double_as_longlong(x)); }
 GM_FN double f_from_bits(uint64_t u) { return __longlong_as_double(static_cast<long long>(u)); }
 GM_FN double f_i2d(int k) { return __int2double_rn(k); }
@@ -89,6 +92,11 @@ GM_FN SinCosRow2 sincos_row2(int i) {
   return SinCosRow2{a.x, a.y, b.x, b.y};
 }
 GM_FN double f_sel(bool c, double a, double b) { return c ? a : b; }
+GM_FN void exp_row(int i, uint64_t& tail, uint64_t& sbits) {
+  const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(&g_exp_tab[2 * i]));
+  tail = v.x; sbits = v.y;
+}
+GM_FN double exp_out_of_range(double x) { return ::exp(x); }
 #define GM_LOG_POLY c_log_poly
 #define GM_LOG_POLY1 c_log_poly1
 #else
@@ -96,6 +104,7 @@ GM_FN double f_fma(double a, double b, double c) { return __builtin_fma(a, b, c)
 GM_FN double f_add(double a, double b) { volatile double r = a + b; return r; }
 GM_FN double f_sub(double a, double b) { volatile double r = a - b; return r; }
 GM_FN double f_mul(double a, double b) { volatile double r = a * b; return r; }
+GM_FN double f_div(double a, double b) { volatile double r = a / b; return r; }
 GM_FN uint64_t f_bits(double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; }
 GM_FN double f_from_bits(uint64_t u) { double x; std::memcpy(&x, &u, 8); return x; }
 GM_FN double f_i2d(int k) { return static_cast<double>(k); }
@@ -105,6 +114,8 @@ GM_FN SinCosRow sincos_row(int k) {
 }
 GM_FN SinCosRow2 sincos_row2(int i) { return h_sincos_rows[i]; }
 GM_FN double f_sel(bool c, double a, double b) { return c ? a : b; }
+GM_FN void exp_row(int i, uint64_t& tail, uint64_t& sbits) { tail = h_exp_tab[2 * i]; sbits = h_exp_tab[2 * i + 1]; }
+GM_FN double exp_out_of_range(double x) { return __builtin_exp(x); }
 #define GM_LOG_POLY h_log_poly
 #define GM_LOG_POLY1 h_log_poly1
 #endif
@@ -232,6 +243,222 @@ GM_FN void log_positive_normal_batch(const double (&x)[N], double (&lg)[N]) {
 #endif
     for (int j = 0; j < N; ++j) lg[j] = (low == (1u << j)) ? r : lg[j];
     pend ^= low;
+  }
+}
+
+// ============================================================================
+// exp
+// ============================================================================
+// sysdeps/ieee754/dbl-64/e_exp.c (Szabolcs Nagy): x = k ln2 / 128 + r, 2^(k/128) from
+// a 128-row table {tail, scale bits}, degree-5 polynomial in r; the FMA build's
+// fused operations written out.  2^-54 <= |x| < 512 here; smaller arguments give
+// 1 + x as in the library; larger ones (over / underflow handling, results that
+// are 0, inf or next to the subnormal range) go to the platform's exp.
+GM_FN double exp(double x) {
+  const uint32_t abstop = static_cast<uint32_t>(f_bits(x) >> 52) & 0x7ffu;
+  if (abstop - 0x3c9u > 0x3eu) {
+    if (abstop < 0x3c9u) return f_add(1.0, x);          // |x| < 2^-54
+    return exp_out_of_range(x);
+  }
+  const double zs = f_fma(x, GLIBC_EXP_INVLN2N, GLIBC_EXP_SHIFT);
+  const uint64_t ki = f_bits(zs);
+  const double kd = f_sub(zs, GLIBC_EXP_SHIFT);
+  double r = f_fma(kd, GLIBC_EXP_NEGLN2HIN, x);
+  r = f_fma(kd, GLIBC_EXP_NEGLN2LON, r);
+  uint64_t tail_bits, sbits;
+  exp_row(static_cast<int>(ki & 127u), tail_bits, sbits);
+  sbits += ki << 45;
+  const double p23 = f_fma(r, GLIBC_EXP_C3, GLIBC_EXP_C2);
+  const double tr = f_add(r, f_from_bits(tail_bits));
+  const double r2 = f_mul(r, r);
+  const double p45 = f_fma(r, GLIBC_EXP_C5, GLIBC_EXP_C4);
+  const double lo = f_fma(p23, r2, tr);
+  const double tmp = f_fma(f_mul(r2, r2), p45, lo);
+  const double scale = f_from_bits(sbits);
+  return f_fma(scale, tmp, scale);
+}
+
+// ============================================================================
+// lgamma (positive arguments)
+// ============================================================================
+// sysdeps/ieee754/dbl-64/e_lgamma_r.c (fdlibm's lgamma): not a multiarch
+// function, so the library's build has no FMA contraction -- every operator
+// below is one IEEE operation, in the published order.  Its internal log() IS
+// the ifunc'ed one (log above).  0 < x < 2: three polynomial / rational pieces
+// around the minimum tc = 1.4616; 2 <= x < 8: rational in the fractional part plus
+// log of the product (y + 2) ... (y + i - 1); 8 <= x < 2^58: Stirling in 1 / x;
+// beyond: x (log x - 1).  Negative, zero, infinite and NaN arguments are the
+// caller's business (samplers.cuh sends them to the toolkit's lgamma).
+// 2 < x < 8 (x == 2 is answered before): rational in the fractional part, plus
+// the log of (y + 2) ... (y + i - 1)
+GM_FN double lgamma_2_to_8(double x) {
+  double r;
+  const int i = static_cast<int>(x);
+  const double y = f_sub(x, f_i2d(i));
+  double p = f_add(GLIBC_LG_S5, f_mul(y, GLIBC_LG_S6));
+  p = f_add(GLIBC_LG_S4, f_mul(y, p));
+  p = f_add(GLIBC_LG_S3, f_mul(y, p));
+  p = f_add(GLIBC_LG_S2, f_mul(y, p));
+  p = f_add(GLIBC_LG_S1, f_mul(y, p));
+  p = f_add(GLIBC_LG_S0, f_mul(y, p));
+  p = f_mul(y, p);
+  double q = f_add(GLIBC_LG_R5, f_mul(y, GLIBC_LG_R6));
+  q = f_add(GLIBC_LG_R4, f_mul(y, q));
+  q = f_add(GLIBC_LG_R3, f_mul(y, q));
+  q = f_add(GLIBC_LG_R2, f_mul(y, q));
+  q = f_add(GLIBC_LG_R1, f_mul(y, q));
+  q = f_add(1.0, f_mul(y, q));
+  r = f_add(f_mul(0.5, y), f_div(p, q));
+  if (i >= 3) {                                             // lgamma(1 + s) = log(s) + lgamma(s)
+    double z = 1.0;
+    if (i >= 7) z = f_mul(z, f_add(y, 6.0));
+    if (i >= 6) z = f_mul(z, f_add(y, 5.0));
+    if (i >= 5) z = f_mul(z, f_add(y, 4.0));
+    if (i >= 4) z = f_mul(z, f_add(y, 3.0));
+    z = f_mul(z, f_add(y, 2.0));
+    r = f_add(r, log(z));
+  }
+  return r;
+}
+
+// 8 <= x < 2^58: (x - 1/2)(log x - 1) + w(1 / x)
+GM_FN double lgamma_stirling(double x) {
+  const double t = log_main(f_bits(x));         // x >= 8: log()'s main path, no window, no special case
+  const double z = f_div(1.0, x);
+  const double y = f_mul(z, z);
+  double w = f_add(GLIBC_LG_W5, f_mul(y, GLIBC_LG_W6));
+  w = f_add(GLIBC_LG_W4, f_mul(y, w));
+  w = f_add(GLIBC_LG_W3, f_mul(y, w));
+  w = f_add(GLIBC_LG_W2, f_mul(y, w));
+  w = f_add(GLIBC_LG_W1, f_mul(y, w));
+  w = f_add(GLIBC_LG_W0, f_mul(z, w));
+  return f_add(f_mul(f_sub(x, 0.5), f_sub(t, 1.0)), w);
+}
+
+GM_FN double lgamma_positive(double x) {
+  const uint32_t ix = static_cast<uint32_t>(f_bits(x) >> 32) & 0x7fffffffu;
+  const uint32_t lx = static_cast<uint32_t>(f_bits(x));
+  if (ix < 0x3b900000u) return f_neg(log(x));                 // x < 2^-70
+  if ((((ix - 0x3ff00000u) | lx) == 0) || (((ix - 0x40000000u) | lx) == 0)) return 0.0;      // 1 and 2
+  double r;
+  if (ix < 0x40000000u) {                                     // x < 2
+    double y;
+    int i;
+    if (ix <= 0x3feccccc) {                                   // lgamma(x) = lgamma(x + 1) - log(x)
+      r = f_neg(log(x));
+      if (ix >= 0x3FE76944u) { y = f_sub(1.0, x); i = 0; }
+      else if (ix >= 0x3FCDA661u) { y = f_sub(x, GLIBC_LG_TC_M1); i = 1; }
+      else { y = x; i = 2; }
+    } else {
+      r = 0.0;
+      if (ix >= 0x3FFBB4C3u) { y = f_sub(2.0, x); i = 0; }    // [1.7316, 2]
+      else if (ix >= 0x3FF3B4C4u) { y = f_sub(x, GLIBC_LG_TC); i = 1; }      // [1.23, 1.73]
+      else { y = f_sub(x, 1.0); i = 2; }
+    }
+    if (i == 0) {
+      const double z = f_mul(y, y);
+      double p1 = f_add(GLIBC_LG_A8, f_mul(z, GLIBC_LG_A10));
+      p1 = f_add(GLIBC_LG_A6, f_mul(z, p1));
+      p1 = f_add(GLIBC_LG_A4, f_mul(z, p1));
+      p1 = f_add(GLIBC_LG_A2, f_mul(z, p1));
+      p1 = f_add(GLIBC_LG_A0, f_mul(z, p1));
+      double p2 = f_add(GLIBC_LG_A9, f_mul(z, GLIBC_LG_A11));
+      p2 = f_add(GLIBC_LG_A7, f_mul(z, p2));
+      p2 = f_add(GLIBC_LG_A5, f_mul(z, p2));
+      p2 = f_add(GLIBC_LG_A3, f_mul(z, p2));
+      p2 = f_add(GLIBC_LG_A1, f_mul(z, p2));
+      p2 = f_mul(z, p2);
+      const double p = f_add(f_mul(y, p1), p2);
+      r = f_add(r, f_sub(p, f_mul(0.5, y)));
+    } else if (i == 1) {
+      const double z = f_mul(y, y);
+      const double w = f_mul(z, y);
+      double p1 = f_add(GLIBC_LG_T9, f_mul(w, GLIBC_LG_T12));
+      p1 = f_add(GLIBC_LG_T6, f_mul(w, p1));
+      p1 = f_add(GLIBC_LG_T3, f_mul(w, p1));
+      p1 = f_add(GLIBC_LG_T0, f_mul(w, p1));
+      double p2 = f_add(GLIBC_LG_T10, f_mul(w, GLIBC_LG_T13));
+      p2 = f_add(GLIBC_LG_T7, f_mul(w, p2));
+      p2 = f_add(GLIBC_LG_T4, f_mul(w, p2));
+      p2 = f_add(GLIBC_LG_T1, f_mul(w, p2));
+      double p3 = f_add(GLIBC_LG_T11, f_mul(w, GLIBC_LG_T14));
+      p3 = f_add(GLIBC_LG_T8, f_mul(w, p3));
+      p3 = f_add(GLIBC_LG_T5, f_mul(w, p3));
+      p3 = f_add(GLIBC_LG_T2, f_mul(w, p3));
+      const double p = f_sub(f_mul(z, p1), f_sub(GLIBC_LG_TT, f_mul(w, f_add(p2, f_mul(y, p3)))));
+      r = f_add(r, f_add(GLIBC_LG_TF, p));
+    } else {
+      double p1 = f_add(GLIBC_LG_U4, f_mul(y, GLIBC_LG_U5));
+      p1 = f_add(GLIBC_LG_U3, f_mul(y, p1));
+      p1 = f_add(GLIBC_LG_U2, f_mul(y, p1));
+      p1 = f_add(GLIBC_LG_U1, f_mul(y, p1));
+      p1 = f_add(GLIBC_LG_U0, f_mul(y, p1));
+      p1 = f_mul(y, p1);
+      double p2 = f_add(GLIBC_LG_V4, f_mul(y, GLIBC_LG_V5));
+      p2 = f_add(GLIBC_LG_V3, f_mul(y, p2));
+      p2 = f_add(GLIBC_LG_V2, f_mul(y, p2));
+      p2 = f_add(GLIBC_LG_V1, f_mul(y, p2));
+      p2 = f_add(1.0, f_mul(y, p2));
+      r = f_add(r, f_add(f_mul(-0.5, y), f_div(p1, p2)));
+    }
+    return r;
+  }
+  if (ix < 0x40200000u) return lgamma_2_to_8(x);               // 2 <= x < 8
+  if (ix < 0x43900000u) return lgamma_stirling(x);            // 8 <= x < 2^58
+  return f_mul(x, f_sub(log(x), 1.0));                        // 2^58 <= x
+}
+
+// N lgammas of positive finite arguments at once.  The three ranges of the
+// function are three different programs; lanes with arguments in different
+// ranges serialise them, and a density with six non-integer lgammas per
+// observation (beta-binomial) pays 6 x (all three).  Here the Stirling range --
+// where most arguments of the count densities live -- is evaluated for all N
+// arguments without a branch (the formula is harmless, if meaningless, below 8),
+// and the arguments of the other two ranges are then worked off in two loops that
+// take ONE pending argument per lane per trip.  Same operations on the same
+// values as N calls of lgamma_positive().
+template <int N>
+GM_FN void lgamma_positive_batch(const double (&x)[N], double (&out)[N]) {
+  unsigned pend_mid = 0, pend_low = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < N; ++i) {
+    const uint32_t ix = static_cast<uint32_t>(f_bits(x[i]) >> 32) & 0x7fffffffu;
+    const uint32_t lx = static_cast<uint32_t>(f_bits(x[i]));
+    const bool stirling = ix >= 0x40200000u && ix < 0x43900000u;
+    const bool mid = ix >= 0x40000000u && ix < 0x40200000u && ((ix - 0x40000000u) | lx) != 0;
+    if (mid) pend_mid |= 1u << i;
+    if (!stirling && !mid) pend_low |= 1u << i;
+    out[i] = lgamma_stirling(x[i]);
+  }
+  while (pend_mid) {
+    const unsigned low = pend_mid & (0u - pend_mid);
+    double xi = x[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 1; j < N; ++j) xi = (low == (1u << j)) ? x[j] : xi;
+    const double r = lgamma_2_to_8(xi);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < N; ++j) out[j] = (low == (1u << j)) ? r : out[j];
+    pend_mid ^= low;
+  }
+  while (pend_low) {                 // below 2, exactly 2, or 2^58 and above
+    const unsigned low = pend_low & (0u - pend_low);
+    double xi = x[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 1; j < N; ++j) xi = (low == (1u << j)) ? x[j] : xi;
+    const double r = lgamma_positive(xi);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < N; ++j) out[j] = (low == (1u << j)) ? r : out[j];
+    pend_low ^= low;
   }
 }
 

@@ -233,8 +233,8 @@ __device__ __forceinline__ void zig_word(ZigLane<T, OutT>& L, uint32_t zig_saddr
     } else {
       // the reference's own evaluation (hdr/normal_ziggurat.hpp:104-107)
       const double xi = g_zig_x[layer], x1 = g_zig_x[layer + 1];
-      const double g0 = exp(-0.5 * (xi * xi - z * z));
-      const double g1 = exp(-0.5 * (x1 * x1 - z * z));
+      const double g0 = m_exp(-0.5 * (xi * xi - z * z));
+      const double g1 = m_exp(-0.5 * (x1 * x1 - z * z));
       wemit = g1 + r * (g0 - g1) < 1.0;
     }
   }

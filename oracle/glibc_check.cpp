@@ -27,6 +27,8 @@ static inline uint64_t bits(double x) { uint64_t u; std::memcpy(&u, &x, 8); retu
 //      3: cos of 2 pi u, u in (0, 1]  (the Box-Muller angle)
 //      4: cos of values in [-8, 8]
 //      5: log of random bit patterns (special cases: negative, NaN, inf, subnormal)
+//      13, 14: exp on [-700, 700] and on every magnitude below 2
+//      9-12: lgamma of positive arguments: (0, 10), any positive normal, (0.5, 300.5), integers and halves
 //      6, 7, 8: the lock-step formulation of cos on the Box-Muller angle, on
 //         [-1000, 1000], on log-uniform magnitudes below 1.0e8
 // Returns the number of arguments whose result differs in any bit; the first
@@ -41,6 +43,7 @@ extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
     for (int64_t j = 0; j < m; ++j) {
       const uint64_t w = splitmix(s);
       double x, got, want;
+      int sg = 0;
       const double u = static_cast<double>(w >> 11) * 0x1p-53 + 0x1p-54;
       switch (kind) {
         case 0: x = u; got = mb200::glibc::log_positive_normal(x); want = std::log(x); break;
@@ -53,6 +56,15 @@ extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
         case 7: x = 2000 * u - 1000; got = mb200::glibc::cos_medium_lockstep(x); want = std::cos(x); break;
         case 8: x = from_bits((w >> 1) % 0x4199000000000000ull);        // any magnitude below 1.0e8, log-uniform
                 got = mb200::glibc::cos_medium_lockstep(x); want = std::cos(x); break;
+        case 9: x = 10 * u; got = mb200::glibc::lgamma_positive(x); want = lgamma_r(x, &sg); break;        // every piece below 8
+        case 10: x = from_bits((w >> 1) % 0x7fe0000000000000ull + 0x0010000000000000ull);                   // any positive normal
+                 got = mb200::glibc::lgamma_positive(x); want = lgamma_r(x, &sg); break;
+        case 11: x = 0.5 + 300 * u; got = mb200::glibc::lgamma_positive(x); want = lgamma_r(x, &sg); break;  // the densities' range
+        case 12: x = static_cast<double>(1 + (w >> 40) % 4096) + ((w & 1) ? 0.5 : 0.0);                      // integers and halves
+                 got = mb200::glibc::lgamma_positive(x); want = lgamma_r(x, &sg); break;
+        case 13: x = 1400 * u - 700; got = mb200::glibc::exp(x); want = std::exp(x); break;
+        case 14: x = from_bits(w & 0xbfffffffffffffffull);                                   // any exponent below 2, both signs
+                 got = mb200::glibc::exp(x); want = std::exp(x); break;
         default: x = from_bits(w); got = mb200::glibc::log(x); want = std::log(x); break;
       }
       const bool same = bits(got) == bits(want) || (got != got && want != want);
@@ -83,11 +95,36 @@ extern "C" int64_t gm_compare_log_batch(uint64_t seed, int64_t n) {
   }
   return mism;
 }
+// lgamma_positive_batch<6> against six single calls of libm's lgamma, n groups
+extern "C" int64_t gm_compare_lgamma_batch(uint64_t seed, int64_t n) {
+  int64_t mism = 0;
+#pragma omp parallel for reduction(+ : mism) schedule(static)
+  for (int64_t c = 0; c < n; ++c) {
+    uint64_t s = seed + 0x9e3779b9ull * static_cast<uint64_t>(c);
+    double x[6], lg[6];
+    for (int i = 0; i < 6; ++i) {
+      const uint64_t w = splitmix(s);
+      const double u = static_cast<double>(w >> 11) * 0x1p-53 + 0x1p-54;
+      switch (w & 7) {                      // every range, exact 1 and 2, huge
+        case 0: x[i] = 2 * u; break;
+        case 1: x[i] = 2 + 6 * u; break;
+        case 2: x[i] = (w & 8) ? 1.0 : 2.0; break;
+        case 3: x[i] = 0x1p58 * (1 + u); break;
+        default: x[i] = 8 + 300 * u; break;
+      }
+    }
+    mb200::glibc::lgamma_positive_batch<6>(x, lg);
+    for (int i = 0; i < 6; ++i) { int sg; mism += bits(lg[i]) != bits(lgamma_r(x[i], &sg)); }
+  }
+  return mism;
+}
+extern "C" double gm_exp(double x) { return mb200::glibc::exp(x); }
+extern "C" double gm_lgamma(double x) { return mb200::glibc::lgamma_positive(x); }
 extern "C" double gm_log(double x) { return mb200::glibc::log(x); }
 extern "C" double gm_cos(double x) { return mb200::glibc::cos_medium(x); }
 extern "C" double gm_cos_lockstep(double x) { return mb200::glibc::cos_medium_lockstep(x); }
 
-// fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt of the live libm, elementwise
+// fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt, 4 = lgamma of the live libm, elementwise
 extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
@@ -95,6 +132,7 @@ extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {
       case 0: y[i] = std::log(x[i]); break;
       case 1: y[i] = std::cos(x[i]); break;
       case 2: y[i] = std::exp(x[i]); break;
+      case 4: { int sg; y[i] = lgamma_r(x[i], &sg); break; }
       default: y[i] = std::sqrt(x[i]); break;
     }
   }

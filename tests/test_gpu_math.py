@@ -42,7 +42,7 @@ def libm():
     def call(fn, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)
-        lib.gm_libm({"log": 0, "cos": 1, "exp": 2, "sqrt": 3}[fn], x.ctypes.data, y.ctypes.data, x.size)
+        lib.gm_libm({"log": 0, "cos": 1, "exp": 2, "sqrt": 3, "lgamma": 4}[fn], x.ctypes.data, y.ctypes.data, x.size)
         return y
     return call
 
@@ -128,6 +128,47 @@ def test_cos_on_corner_angles(probe, libm):
     x = x[(x >= 0) & (x <= two_pi)]
     assert same_bits(probe("cos_0_2pi", x), libm("cos", x)).all()
     assert probe("cos_0_2pi", np.array([0.0]))[0] == 1.0
+
+
+def test_lgamma_is_glibc_bit_for_bit(probe, libm):
+    """m_lgamma (glibc's e_lgamma_r.c restated, detail/glibc_math.cuh) on every
+    piece of the function: (0, 2) with its three sub-intervals and the 2^-70
+    cut, [2, 8), Stirling above 8, the x (log x - 1) range, integers (the table)
+    and half-integers; zero / negative / non-finite arguments take the toolkit's
+    routine and only have to agree in value."""
+    rs = np.random.default_rng(6)
+    n = max(1, N // 10)
+    x = np.concatenate([rs.uniform(0, 10, n), rs.uniform(0.5, 300.5, n), np.exp(rs.uniform(-200, 700, n)),
+                        np.arange(1, 20000, dtype=np.float64), np.arange(1, 2000) + 0.5,
+                        np.array([2.0 ** -71, 2.0 ** -70, 0.23, 0.2316, 0.7316, 0.9, 1.0, 1.2316, 1.4616321449683622,
+                                  1.7316, 2.0, 3.0, 7.999999, 8.0, 2.0 ** 58, 1e300])])
+    for b in (0.23163998, 0.73163998, 0.9, 1.23164, 1.73163998, 2.0, 8.0):          # both sides of every cut
+        v = np.float64(b).view(np.uint64)
+        x = np.concatenate([x, (v + np.arange(-3000, 3000).astype(np.int64).astype(np.uint64)).view(np.float64)])
+    ok = same_bits(probe("lgamma", x), libm("lgamma", x))
+    assert ok.all(), "first offender x = %s" % x[~ok][0].hex()
+    odd = np.array([0.0, -0.5, -2.5, np.inf])
+    got = probe("lgamma", odd)
+    assert got[0] == np.inf and got[3] == np.inf
+    assert np.allclose(got[1:3], libm("lgamma", odd[1:3]), rtol=1e-14)
+
+
+def test_exp_is_glibc_bit_for_bit(probe, libm):
+    """m_exp (glibc's e_exp.c restated) on [-512, 512) and tiny arguments: the same
+    bits as the host's libm; 512 <= |x| takes the toolkit's exp (results 0, inf
+    or next to the subnormal range) and has to agree to 1 ulp."""
+    rs = np.random.default_rng(7)
+    n = max(1, N // 10)
+    x = np.concatenate([rs.uniform(-512, 512, n), rs.uniform(-40, 3, n), rs.uniform(-1, 1, n) * 2.0 ** -rs.integers(0, 70, n).astype(np.float64),
+                        np.array([0.0, -0.0, 1.0, -1.0, 2.0 ** -54, 2.0 ** -55, -2.0 ** -60, 511.999, -511.999, 709.0, -708.0])])
+    inner = (np.abs(x) < 512)
+    got, want = probe("exp", x), libm("exp", x)
+    ok = same_bits(got[inner], want[inner])
+    assert ok.all(), "first offender x = %s" % x[inner][~ok][0].hex()
+    far = np.array([512.0, 600.0, 709.7, -600.0, -708.3, -740.0, -750.0, 720.0])
+    g, w = probe("exp", far), libm("exp", far)
+    with np.errstate(invalid="ignore"):
+        assert ((g == w) | (np.abs(g - w) <= np.abs(np.spacing(w)))).all()
 
 
 def test_sqrt_is_correctly_rounded(probe):

@@ -22,6 +22,9 @@ Tables:
     scalar constants of s_sin.c / branred (big, hp0, hp1, mp1, mp2, pp3, pp4,
     hpinv, toint, sn3, sn5, cs2, cs4, cs6, s1..s5) -- written from their
     published values and CHECKED to be present in the library's .rodata.
+    __exp_data      invln2N, shift, -ln2/N (hi, lo), C2..C5, tab[128] {tail, scale}
+    e_lgamma_r.c    the 65 polynomial coefficients of fdlibm's lgamma (a, t, u, v,
+    s, r, w families, tc, tf, tt), read from the function's constant pool.
 
 The tables are located by signature (ln2hi followed by ln2lo; {0, 0, 1, 0,
 sin(1/128)}), not by address, so another build of glibc 2.39 works too.
@@ -125,8 +128,59 @@ def main(out=None):
         v = float.fromhex(hx)
         if find_doubles(blob, off, size, [v]) < 0:
             missing.append(name)
+    # ---- e_lgamma_r.c (fdlibm) constants: the compiler laid them out in one pool, in
+    # order of first use; anchored on a0 = Euler's gamma - 1/2 and read by offset.
+    # A constant the code SUBTRACTS is stored as its magnitude (x + (-c) == x - c bit
+    # for bit), so the signs of the published fdlibm values are restored here.
+    a0 = float.fromhex("0x1.3c467e37db0c8p-4")
+    k = find_doubles(blob, off, size, [float.fromhex("0x1.13e001a5562a7p-4"), a0])     # a2, a0
+    if k < 0:
+        raise SystemExit("lgamma constant pool not found")
+    base = k + 8                                    # file offset of a0
+    def at(rel):
+        return dbl(blob, base + rel, 1)[0]
+    LG = {}
+    for name, rel in (("a0", 0), ("a1", 0x30), ("a2", -0x8), ("a3", 0x28), ("a4", -0x10), ("a5", 0x20), ("a6", -0x18),
+                      ("a7", 0x18), ("a8", -0x20), ("a9", 0x10), ("a10", -0x28), ("a11", 0x8),
+                      ("tc", -0x30), ("tc_m1", -0x38), ("tt", 0xb0),
+                      ("t0", 0x58), ("t3", -0x50), ("t6", 0x48), ("t9", -0x40), ("t12", 0x38),
+                      ("t2", 0x80), ("t5", -0x78), ("t8", 0x70), ("t11", -0x68), ("t14", 0x60),
+                      ("t1", -0xa8), ("t4", 0xa0), ("t7", -0x98), ("t10", 0x90), ("t13", 0x88),
+                      ("u1", 0xd8), ("u2", 0xd0), ("u3", 0xc8), ("u4", 0xc0), ("u5", 0xb8),
+                      ("v1", 0x100), ("v2", 0xf8), ("v3", 0xf0), ("v4", 0xe8), ("v5", 0xe0),
+                      ("s1", 0x138), ("s2", 0x130), ("s3", 0x128), ("s4", 0x120), ("s5", 0x118), ("s6", 0x110),
+                      ("r1", 0x168), ("r2", 0x160), ("r3", 0x158), ("r4", 0x150), ("r5", 0x148), ("r6", 0x140),
+                      ("w0", 0x1b8), ("w1", 0x1b0), ("w2", -0x1a8), ("w3", 0x1a0), ("w4", -0x198), ("w5", 0x190),
+                      ("w6", 0x188)):
+        neg = rel < 0 and name[0] in "tw" and name not in ("tc", "tc_m1")
+        v = at(-rel if neg else rel)
+        LG[name] = -v if neg else v
+    LG["u0"] = -LG["a0"]
+    LG["s0"] = -LG["a0"]
+    LG["tf"] = float.fromhex("-0x1.f19b9bcc38a42p-4")
+    if find_doubles(blob, off, size, [-LG["tf"]]) < 0:
+        raise SystemExit("lgamma: tf not found")
+    # the published values (s_lgamma / e_lgamma_r.c): spot checks of the layout
+    assert abs(LG["tc"] - 1.46163214496836224576) < 1e-18 and abs(LG["tc_m1"] - 0.46163214496836225) < 1e-17
+    assert abs(LG["w0"] - 0.41893853320467274178) < 1e-17 and abs(LG["w1"] - 1 / 12) < 1e-14 and LG["w2"] < 0
+    assert abs(LG["t0"] - 0.483836122723810047042) < 1e-16 and LG["t1"] < 0 and LG["t3"] < 0 and LG["t13"] < 0
+    assert abs(LG["a1"] - 0.322467033424113591611) < 1e-16 and abs(LG["u1"] - 0.632827064025093366517) < 1e-16
+    assert abs(LG["s1"] - 0.214982415960608852501) < 1e-16 and abs(LG["r1"] - 1.39200533467621045958) < 1e-15
+    # ---- __exp_data (e_exp.c, Szabolcs Nagy's exp, N = 128): invln2N, shift, -ln2hi/N,
+    # -ln2lo/N, C2..C5, [pad], tab[2 N] = {tail, scale bits} -- anchored on InvLn2N
+    invln2n = float.fromhex("0x1.71547652b82fep7")
+    e = find_doubles(blob, off, size, [invln2n, float.fromhex("0x1.8p52")])
+    if e < 0:
+        raise SystemExit("exp data signature not found")
+    EX = dict(zip(("invln2n", "shift", "negln2hin", "negln2lon", "c2", "c3", "c4", "c5"), dbl(blob, e, 8)))
+    assert abs(EX["c2"] - 0.5) < 1e-9 and abs(EX["c3"] - 1 / 6) < 1e-9 and abs(EX["negln2hin"] + math.log(2) / 128) < 1e-12
+    exptab = list(struct.unpack_from("<256Q", blob, e + 0xb0))
+    assert exptab[0] == 0 and exptab[1] == 0x3ff0000000000000
+    for i in range(128):          # scale bits + (i << 45) is 2^(i/128); tail is its rounding error
+        sc = struct.unpack("<d", struct.pack("<Q", exptab[2 * i + 1] + (i << 45)))[0]
+        assert abs(sc - 2.0 ** (i / 128)) < 1e-15, i
     if out is None:
-        return dict(ln2hi=ln2hi, ln2lo=ln2lo, A=A, B=B, T=T, sincos=sct, missing=missing,
+        return dict(ln2hi=ln2hi, lgamma=LG, ln2lo=ln2lo, A=A, B=B, T=T, sincos=sct, missing=missing,
                     log_addr=addr + (i - off), sincos_addr=addr + (j - off))
     if missing:
         raise SystemExit("constants not found in libm .rodata: %s" % missing)
@@ -163,6 +217,16 @@ def main(out=None):
     L[-1] = L[-1][:-3] + " }"
     for name, hx in consts.items():
         L.append("#define GLIBC_SC_%s %s" % (name.upper(), fh(float.fromhex(hx))))
+    L.append("/* __exp_data: scalars, then tab[128] = {tail bits, scale bits - (i << 45)} */")
+    for name, v in EX.items():
+        L.append("#define GLIBC_EXP_%s %s" % (name.upper(), fh(v)))
+    L.append("#define GLIBC_EXP_TAB { \\")
+    for i in range(0, 256, 4):
+        L.append("  " + ", ".join("0x%016xull" % v for v in exptab[i:i + 4]) + ", \\")
+    L[-1] = L[-1][:-3] + " }"
+    L.append("/* e_lgamma_r.c (fdlibm) constants, signs as published */")
+    for name in sorted(LG, key=lambda n: (n.rstrip("0123456789_m"), int("".join(c for c in n if c.isdigit()) or 0))):
+        L.append("#define GLIBC_LG_%s %s" % (name.upper(), fh(LG[name])))
     with open(out, "w") as f:
         f.write("\n".join(L) + "\n")
     print("wrote", out)
