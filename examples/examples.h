@@ -50,7 +50,7 @@ int mb200_example_inline_multinomial(mb200_rng* rng, int real_type,
  * (positive normal arguments), 2 = cos_0_2pi (0 <= x <= 2 pi), 3 = sqrt_normal
  * (positive normal arguments), 4 = the toolkit's sqrt, 5 = 1.0 when the examples
  * library was compiled without FMA contraction (monty::random::contraction_is_off),
- * 6 = m_lgamma, 7 = m_exp. */
+ * 6 = m_lgamma, 7 = m_exp, 8 = m_pow(x[i], x[i ^ 1]) (n even). */
 int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n);
 
 /* monty::density::zi_poisson (which = 0; a = lambda), zi_negative_binomial_prob

@@ -173,6 +173,7 @@ __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* 
     case 5: r = monty::random::contraction_is_off() ? 1.0 : 0.0; break;
     case 6: r = mb200::m_lgamma(v); break;
     case 7: r = mb200::m_exp(v); break;
+    case 8: r = mb200::m_pow(v, x[i ^ 1]); break;        // exponent: the neighbouring element
     default: r = 0.0; break;
   }
   y[i] = r;
@@ -180,7 +181,7 @@ __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* 
 }  // namespace
 
 extern "C" int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n) {
-  if (!x_host || !y_host || fn < 0 || fn > 7) return MB200_ERR_ARG;
+  if (!x_host || !y_host || fn < 0 || fn > 8) return MB200_ERR_ARG;
   double *dx = nullptr, *dy = nullptr;
   int rc = MB200_OK;
   if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&dy, n * sizeof(double)) != cudaSuccess ||

@@ -163,7 +163,7 @@ template <typename T> __device__ T dens_cauchy(T x, T location, T scale, bool lg
   // monty::math::log(M_PI) is the double log, so the sum is a double and
   // maybe_log<double> is what gets deduced
   const T q = (x - location) / scale;
-  const T q2 = sizeof(T) == 4 ? static_cast<T>(pow(static_cast<double>(q), 2.0)) : static_cast<T>(pow(q, 2.0));
+  const T q2 = sizeof(T) == 4 ? static_cast<T>(m_pow(static_cast<double>(q), 2.0)) : static_cast<T>(m_pow(static_cast<double>(q), 2.0));
   const double ret = -m_log(M_PI) - m_log(scale) - m_log1p(q2);
   return lg ? static_cast<T>(ret) : static_cast<T>(m_exp(ret));
 }

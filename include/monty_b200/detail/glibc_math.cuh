@@ -49,12 +49,15 @@ namespace glibc {
 struct alignas(16) LogRow { double invc, logc; };
 struct SinCosRow { double sn, ssn, cs, ccs; };
 struct alignas(32) SinCosRow2 { double P, p, Q, q; };    // lock-step rows, see sincos_core
+struct PowLogRow { double invc, logc, logctail; };
 
 #if defined(__CUDACC__)
 static __device__ const LogRow g_log_tab[128] = GLIBC_LOG_TAB;
 static __device__ __align__(32) const double g_sincos_tab[440] = GLIBC_SINCOS_TAB;
 static __device__ const SinCosRow2 g_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static __device__ __align__(16) const unsigned long long g_exp_tab[256] = GLIBC_EXP_TAB;
+static __device__ const PowLogRow g_pow_tab[128] = GLIBC_POW_TAB;
+static __constant__ double c_pow_poly[7] = GLIBC_POW_POLY;
 static __constant__ double c_log_poly[5] = GLIBC_LOG_POLY;
 static __constant__ double c_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
@@ -63,6 +66,8 @@ static const LogRow h_log_tab[128] = GLIBC_LOG_TAB;
 static const double h_sincos_tab[440] = GLIBC_SINCOS_TAB;
 static const SinCosRow2 h_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static const unsigned long long h_exp_tab[256] = GLIBC_EXP_TAB;
+static const PowLogRow h_pow_tab[128] = GLIBC_POW_TAB;
+static const double h_pow_poly[7] = GLIBC_POW_POLY;
 static const double h_log_poly[5] = GLIBC_LOG_POLY;
 static const double h_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
@@ -97,6 +102,11 @@ GM_FN void exp_row(int i, uint64_t& tail, uint64_t& sbits) {
   tail = v.x; sbits = v.y;
 }
 GM_FN double exp_out_of_range(double x) { return ::exp(x); }
+GM_FN PowLogRow pow_row(int i) {
+  return PowLogRow{__ldg(&g_pow_tab[i].invc), __ldg(&g_pow_tab[i].logc), __ldg(&g_pow_tab[i].logctail)};
+}
+GM_FN double pow_special(double x, double y) { return ::pow(x, y); }
+#define GM_POW_POLY c_pow_poly
 #define GM_LOG_POLY c_log_poly
 #define GM_LOG_POLY1 c_log_poly1
 #else
@@ -116,6 +126,9 @@ GM_FN SinCosRow2 sincos_row2(int i) { return h_sincos_rows[i]; }
 GM_FN double f_sel(bool c, double a, double b) { return c ? a : b; }
 GM_FN void exp_row(int i, uint64_t& tail, uint64_t& sbits) { tail = h_exp_tab[2 * i]; sbits = h_exp_tab[2 * i + 1]; }
 GM_FN double exp_out_of_range(double x) { return __builtin_exp(x); }
+GM_FN PowLogRow pow_row(int i) { return h_pow_tab[i]; }
+GM_FN double pow_special(double x, double y) { return __builtin_pow(x, y); }
+#define GM_POW_POLY h_pow_poly
 #define GM_LOG_POLY h_log_poly
 #define GM_LOG_POLY1 h_log_poly1
 #endif
@@ -276,6 +289,76 @@ GM_FN double exp(double x) {
   const double tmp = f_fma(f_mul(r2, r2), p45, lo);
   const double scale = f_from_bits(sbits);
   return f_fma(scale, tmp, scale);
+}
+
+// ============================================================================
+// pow
+// ============================================================================
+// sysdeps/ieee754/dbl-64/e_pow.c (Szabolcs Nagy): log(x) as hi + lo with ~68 bits
+// from a 128-row table {1/c, log c, tail} and a degree-7 polynomial, y log(x) as
+// ehi + elo, then exp's table and polynomial with the tail folded in; the FMA
+// build's fused operations written out.  Main path only: x positive and normal,
+// 2^-65 <= |y| < 2^63, |y log x| in [2^-54, 512); everything else (zero /
+// negative / subnormal / non-finite x, huge or tiny y, over- and underflow) is
+// the platform's pow -- the samplers raise uniforms to moderate powers.
+GM_FN double pow(double x, double y) {
+  const uint64_t ix = f_bits(x), iy = f_bits(y);
+  const uint32_t topx = static_cast<uint32_t>(ix >> 52), topy = static_cast<uint32_t>(iy >> 52);
+  if (topx - 1u > 0x7fdu || (topy & 0x7ffu) - 0x3beu > 0x7fu) return pow_special(x, y);
+  const double* A = GM_POW_POLY;
+  // log_inline
+  const uint64_t tmp = ix - 0x3fe6955500000000ull;
+  const int i = static_cast<int>((tmp >> 45) & 127);
+  const int k = static_cast<int>(static_cast<int64_t>(tmp) >> 52);
+  const double z = f_from_bits(ix - (tmp & 0xfff0000000000000ull));
+  const double kd = f_i2d(k);
+  const PowLogRow row = pow_row(i);
+  const double t1 = f_fma(kd, GLIBC_LOG_LN2HI, row.logc);
+  const double lo1 = f_fma(kd, GLIBC_LOG_LN2LO, row.logctail);
+  const double r = f_fma(z, row.invc, -1.0);
+  const double ar = f_mul(r, A[0]);
+  const double p12 = f_fma(r, A[2], A[1]);
+  const double p34 = f_fma(r, A[4], A[3]);
+  const double t2 = f_add(r, t1);
+  const double lo2 = f_add(f_sub(t1, t2), r);
+  const double ar2 = f_mul(r, ar);
+  const double ar3 = f_mul(r, ar2);
+  const double lo3 = f_fma(ar, r, -ar2);
+  const double hi = f_add(t2, ar2);
+  const double p56 = f_fma(r, A[6], A[5]);
+  const double lo4 = f_add(f_sub(t2, hi), ar2);
+  double p = f_fma(p56, ar2, p34);
+  p = f_fma(ar2, p, p12);
+  double lo = f_add(lo1, lo2);
+  lo = f_add(lo, lo3);
+  lo = f_add(lo, lo4);
+  lo = f_fma(ar3, p, lo);
+  const double lhi = f_add(hi, lo);
+  const double llo = f_add(f_sub(hi, lhi), lo);
+  // y log(x) = ehi + elo
+  const double ehi = f_mul(y, lhi);
+  double elo = f_fma(lhi, y, -ehi);
+  elo = f_fma(y, llo, elo);
+  // exp_inline
+  const uint32_t abstop = static_cast<uint32_t>(f_bits(ehi) >> 52) & 0x7ffu;
+  if (abstop - 0x3c9u > 0x3eu) return pow_special(x, y);
+  const double zs = f_fma(ehi, GLIBC_EXP_INVLN2N, GLIBC_EXP_SHIFT);
+  const uint64_t ki = f_bits(zs);
+  const double kd2 = f_sub(zs, GLIBC_EXP_SHIFT);
+  double rr = f_fma(kd2, GLIBC_EXP_NEGLN2HIN, ehi);
+  rr = f_fma(kd2, GLIBC_EXP_NEGLN2LON, rr);
+  rr = f_add(elo, rr);
+  uint64_t tail_bits, sbits;
+  exp_row(static_cast<int>(ki & 127u), tail_bits, sbits);
+  sbits += ki << 45;
+  const double q23 = f_fma(rr, GLIBC_EXP_C3, GLIBC_EXP_C2);
+  const double tr = f_add(rr, f_from_bits(tail_bits));
+  const double r2 = f_mul(rr, rr);
+  const double q45 = f_fma(rr, GLIBC_EXP_C5, GLIBC_EXP_C4);
+  const double lo5 = f_fma(q23, r2, tr);
+  const double tmp2 = f_fma(f_mul(r2, r2), q45, lo5);
+  const double scale = f_from_bits(sbits);
+  return f_fma(tmp2, scale, scale);
 }
 
 // ============================================================================

@@ -96,7 +96,7 @@ __device__ T deterministic_value(int dist, const T* p, Rng& rng, bool& used, int
     return b * m_tgamma(1 + 1 / a);
   case MB200_DIST_LOG_NORMAL:                                               // hdr/log_normal.hpp:30-35
     if (!is_finite(a) || !is_finite(b) || b <= 0) { err = kErrParam; return 0; }
-    return m_exp(a + (sizeof(T) == 4 ? static_cast<T>(pow(static_cast<double>(b), 2.0)) : static_cast<T>(pow(b, 2.0))) / 2);
+    return m_exp(a + (sizeof(T) == 4 ? static_cast<T>(m_pow(static_cast<double>(b), 2.0)) : static_cast<T>(m_pow(static_cast<double>(b), 2.0))) / 2);
   case MB200_DIST_BETA_BINOMIAL_PROB:
   case MB200_DIST_BETA_BINOMIAL_AB: {                                       // hdr/beta_binomial.hpp:27-49
     T aa = b, bb = c;

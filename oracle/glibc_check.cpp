@@ -27,6 +27,7 @@ static inline uint64_t bits(double x) { uint64_t u; std::memcpy(&u, &x, 8); retu
 //      3: cos of 2 pi u, u in (0, 1]  (the Box-Muller angle)
 //      4: cos of values in [-8, 8]
 //      5: log of random bit patterns (special cases: negative, NaN, inf, subnormal)
+//      15-17: pow(uniform, (0.05, 12)), pow(any positive normal, (-20, 20)), pow((0, 50), any bit pattern)
 //      13, 14: exp on [-700, 700] and on every magnitude below 2
 //      9-12: lgamma of positive arguments: (0, 10), any positive normal, (0.5, 300.5), integers and halves
 //      6, 7, 8: the lock-step formulation of cos on the Box-Muller angle, on
@@ -65,6 +66,13 @@ extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
         case 13: x = 1400 * u - 700; got = mb200::glibc::exp(x); want = std::exp(x); break;
         case 14: x = from_bits(w & 0xbfffffffffffffffull);                                   // any exponent below 2, both signs
                  got = mb200::glibc::exp(x); want = std::exp(x); break;
+        case 15: x = u; { const double yy = 0.05 + 12 * (static_cast<double>(splitmix(s) >> 11) * 0x1p-53);     // pow(u, 1 / shape)
+                  got = mb200::glibc::pow(x, yy); want = std::pow(x, yy); } break;
+        case 16: x = from_bits((w >> 1) % 0x7fe0000000000000ull + 0x0010000000000000ull);                      // any positive normal base
+                 { const double yy = 40 * (static_cast<double>(splitmix(s) >> 11) * 0x1p-53) - 20;
+                   got = mb200::glibc::pow(x, yy); want = std::pow(x, yy); } break;
+        case 17: x = 50 * u; { const double yy = from_bits(splitmix(s));                                        // any exponent
+                  got = mb200::glibc::pow(x, yy); want = std::pow(x, yy); } break;
         default: x = from_bits(w); got = mb200::glibc::log(x); want = std::log(x); break;
       }
       const bool same = bits(got) == bits(want) || (got != got && want != want);
@@ -118,13 +126,14 @@ extern "C" int64_t gm_compare_lgamma_batch(uint64_t seed, int64_t n) {
   }
   return mism;
 }
+extern "C" double gm_pow(double x, double y) { return mb200::glibc::pow(x, y); }
 extern "C" double gm_exp(double x) { return mb200::glibc::exp(x); }
 extern "C" double gm_lgamma(double x) { return mb200::glibc::lgamma_positive(x); }
 extern "C" double gm_log(double x) { return mb200::glibc::log(x); }
 extern "C" double gm_cos(double x) { return mb200::glibc::cos_medium(x); }
 extern "C" double gm_cos_lockstep(double x) { return mb200::glibc::cos_medium_lockstep(x); }
 
-// fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt, 4 = lgamma of the live libm, elementwise
+// fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt, 4 = lgamma, 5 = pow(x[i], x[i ^ 1]) of the live libm, elementwise
 extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
@@ -133,6 +142,7 @@ extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {
       case 1: y[i] = std::cos(x[i]); break;
       case 2: y[i] = std::exp(x[i]); break;
       case 4: { int sg; y[i] = lgamma_r(x[i], &sg); break; }
+      case 5: y[i] = std::pow(x[i], x[i ^ 1]); break;       // exponent: the neighbouring element (n even)
       default: y[i] = std::sqrt(x[i]); break;
     }
   }

@@ -42,7 +42,7 @@ def libm():
     def call(fn, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)
-        lib.gm_libm({"log": 0, "cos": 1, "exp": 2, "sqrt": 3, "lgamma": 4}[fn], x.ctypes.data, y.ctypes.data, x.size)
+        lib.gm_libm({"log": 0, "cos": 1, "exp": 2, "sqrt": 3, "lgamma": 4, "pow": 5}[fn], x.ctypes.data, y.ctypes.data, x.size)
         return y
     return call
 
@@ -169,6 +169,34 @@ def test_exp_is_glibc_bit_for_bit(probe, libm):
     g, w = probe("exp", far), libm("exp", far)
     with np.errstate(invalid="ignore"):
         assert ((g == w) | (np.abs(g - w) <= np.abs(np.spacing(w)))).all()
+
+
+def test_pow_is_glibc_bit_for_bit(probe, libm):
+    """m_pow (glibc's e_pow.c restated): pow(u, 1 / shape) as the gamma and Weibull
+    samplers call it, general positive bases, and special operands (which take the
+    toolkit's pow and must agree in value)."""
+    rs = np.random.default_rng(8)
+    n = max(2, (N // 20) * 2)
+    x = np.empty(n)
+    x[0::2] = random_reals(rs, n // 2)                   # pow(x[i], x[i ^ 1]): even = base for odd's exponent and vice versa
+    x[1::2] = rs.uniform(0.05, 12, n // 2)
+    got, want = probe("pow", x), libm("pow", x)
+    assert same_bits(got, want).all(), "first offender %s" % x[~same_bits(got, want)][:2]
+    y = np.empty(n)
+    y[0::2] = np.exp(rs.uniform(-300, 300, n // 2))
+    y[1::2] = rs.uniform(0.1, 2.2, n // 2)
+    got, want = probe("pow", y), libm("pow", y)
+    # |y log x| < 512, i.e. results between e^-512 and e^512, is the restated main path;
+    # beyond it the toolkit's pow answers (1 ulp)
+    with np.errstate(divide="ignore"):
+        main = np.isfinite(want) & (want != 0) & (np.abs(np.log(want)) < 511)
+    assert same_bits(got[main], want[main]).all()
+    rest = np.isfinite(want) & ~main
+    assert (np.abs(got[rest] - want[rest]) <= np.abs(np.spacing(want[rest]))).all()
+    odd = np.array([0.0, 2.5, 2.0, 0.0, -2.0, 3.0, 1.0, 1e300, np.inf, 0.5, 4.0, 0.5])
+    g, w = probe("pow", odd), libm("pow", odd)
+    with np.errstate(invalid="ignore"):
+        assert (same_bits(g, w) | (np.abs(g - w) <= np.abs(np.spacing(w)))).all()
 
 
 def test_sqrt_is_correctly_rounded(probe):

@@ -8,12 +8,11 @@ Bars (BASELINE.json north_star):
     attributable to libm ulp differences -- we assert 0 mismatches here;
   * continuous draws (double): within 4 ulp.  The device's log and cos return
     glibc's bits (include/monty_b200/detail/glibc_math.cuh), so every sampler assembled from log,
-    exp, cos, sqrt and IEEE arithmetic alone -- exponential, the three normals,
-    truncated normal, log_normal, gamma with shape >= 1, beta with both shapes
-    >= 1 -- is asserted BIT-IDENTICAL, shifted and scaled parameters included;
-    the ones that also call pow / tan (gamma below shape 1, weibull, cauchy: the
-    toolkit's routines, <= 2 ulp) are held to 4 ulp, cauchy's `location + scale *
-    tan` to 4 eps of the terms it adds;
+    exp, pow, cos, sqrt and IEEE arithmetic alone -- exponential, the three
+    normals, truncated normal, log_normal, gamma, beta, weibull -- is asserted
+    BIT-IDENTICAL, shifted and scaled parameters included; cauchy (tan: the
+    toolkit's routine, <= 2 ulp) is held to 4 eps of the terms `location + scale *
+    tan` adds;
   * float real_type: continuous draws within 1e-6 relative on standard
     parameters.  Integer-valued float draws that go through lgammaf / logf
     with cancellation (Poisson lambda >~ 1e3, hypergeometric H2PE, negative
@@ -32,9 +31,9 @@ pytestmark = pytest.mark.gpu
 
 ALL = sorted(sampler_cases(4))
 CONTINUOUS = [n for n in ALL if n not in INTEGER_VALUED and n not in ("real", "uniform")]
-# log, exp, cos, sqrt and IEEE arithmetic only: the same bits as the reference
+# log, exp, pow, cos, sqrt and IEEE arithmetic only: the same bits as the reference
 BIT_EXACT = {"exponential_rate", "exponential_mean", "normal_box_muller", "normal_polar", "normal_ziggurat",
-             "truncated_normal", "log_normal"}
+             "truncated_normal", "log_normal", "gamma_scale", "gamma_rate", "beta", "weibull"}
 EPS = np.finfo(np.float64).eps
 
 

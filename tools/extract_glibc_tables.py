@@ -22,6 +22,7 @@ Tables:
     scalar constants of s_sin.c / branred (big, hp0, hp1, mp1, mp2, pp3, pp4,
     hpinv, toint, sn3, sn5, cs2, cs4, cs6, s1..s5) -- written from their
     published values and CHECKED to be present in the library's .rodata.
+    __pow_log_data  poly[7], tab[128] {invc, logc, logctail} of pow's own log
     __exp_data      invln2N, shift, -ln2/N (hi, lo), C2..C5, tab[128] {tail, scale}
     e_lgamma_r.c    the 65 polynomial coefficients of fdlibm's lgamma (a, t, u, v,
     s, r, w families, tc, tf, tt), read from the function's constant pool.
@@ -95,6 +96,7 @@ def main(out=None):
     i = find_doubles(blob, off, size, [LN2HI, LN2LO])
     if i < 0:
         raise SystemExit("log table signature not found")
+    log_off = i
     logd = dbl(blob, i, 2 + 5 + 11 + 256)
     ln2hi, ln2lo = logd[0], logd[1]
     A = logd[2:7]
@@ -179,9 +181,20 @@ def main(out=None):
     for i in range(128):          # scale bits + (i << 45) is 2^(i/128); tail is its rounding error
         sc = struct.unpack("<d", struct.pack("<Q", exptab[2 * i + 1] + (i << 45)))[0]
         assert abs(sc - 2.0 ** (i / 128)) < 1e-15, i
+    # ---- __pow_log_data (e_pow.c): ln2hi, ln2lo (the same values as log's), poly[7],
+    # tab[128] = {invc, pad, logc, logctail}: the SECOND occurrence of {ln2hi, ln2lo}
+    pw = find_doubles(blob, log_off + 16, off + size - (log_off + 16), [LN2HI, LN2LO])
+    if pw < 0:
+        raise SystemExit("pow log data signature not found")
+    PW = dbl(blob, pw + 16, 7)
+    assert PW[0] == -0.5 and abs(PW[1] + 2 / 3.0) < 1e-12       # A[0] = -1/2, A[1] = (1/3) * -2 (scaled by powers of -2)
+    powtab = dbl(blob, pw + 0x48, 128 * 4)
+    for k in range(128):
+        invc, pad, logc, tail = powtab[4 * k:4 * k + 4]
+        assert pad == 0.0 and 0.7 < invc < 1.45 and abs(logc + tail - math.log(1 / invc)) < 1e-15, k
     if out is None:
         return dict(ln2hi=ln2hi, lgamma=LG, ln2lo=ln2lo, A=A, B=B, T=T, sincos=sct, missing=missing,
-                    log_addr=addr + (i - off), sincos_addr=addr + (j - off))
+                    log_addr=addr + (log_off - off), sincos_addr=addr + (j - off))
     if missing:
         raise SystemExit("constants not found in libm .rodata: %s" % missing)
     fh = lambda v: float(v).hex()  # noqa: E731
@@ -223,6 +236,12 @@ def main(out=None):
     L.append("#define GLIBC_EXP_TAB { \\")
     for i in range(0, 256, 4):
         L.append("  " + ", ".join("0x%016xull" % v for v in exptab[i:i + 4]) + ", \\")
+    L[-1] = L[-1][:-3] + " }"
+    L.append("/* __pow_log_data: poly[7], tab[128] = {invc, logc, logctail} (the pad word dropped) */")
+    L.append("#define GLIBC_POW_POLY { %s }" % ", ".join(fh(v) for v in PW))
+    L.append("#define GLIBC_POW_TAB { \\")
+    for k in range(128):
+        L.append("  {%s, %s, %s}, \\" % (fh(powtab[4 * k]), fh(powtab[4 * k + 2]), fh(powtab[4 * k + 3])))
     L[-1] = L[-1][:-3] + " }"
     L.append("/* e_lgamma_r.c (fdlibm) constants, signs as published */")
     for name in sorted(LG, key=lambda n: (n.rstrip("0123456789_m"), int("".join(c for c in n if c.isdigit()) or 0))):
