@@ -57,6 +57,14 @@ static __device__ __align__(32) const double g_sincos_tab[440] = GLIBC_SINCOS_TA
 static __device__ const SinCosRow2 g_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static __device__ __align__(16) const unsigned long long g_exp_tab[256] = GLIBC_EXP_TAB;
 static __device__ const PowLogRow g_pow_tab[128] = GLIBC_POW_TAB;
+static __device__ const LogRow g_logf_tab[16] = GLIBC_LOGF_TAB;
+static __device__ __align__(16) const unsigned long long g_expf_tab[32] = GLIBC_EXPF_TAB;
+static __constant__ double c_sincosf_tab[28] = GLIBC_SINCOSF_TAB;
+static __device__ const LogRow g_powf_tab[16] = GLIBC_POWF_TAB;
+static __constant__ double c_powf_poly[5] = GLIBC_POWF_POLY;
+static __constant__ double c_exp2f_poly[3] = GLIBC_EXP2F_POLY;
+static __constant__ double c_logf_poly[3] = GLIBC_LOGF_POLY;
+static __constant__ double c_expf_poly[3] = GLIBC_EXPF_POLY;
 static __constant__ double c_pow_poly[7] = GLIBC_POW_POLY;
 static __constant__ double c_log_poly[5] = GLIBC_LOG_POLY;
 static __constant__ double c_log_poly1[11] = GLIBC_LOG_POLY1;
@@ -67,6 +75,14 @@ static const double h_sincos_tab[440] = GLIBC_SINCOS_TAB;
 static const SinCosRow2 h_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static const unsigned long long h_exp_tab[256] = GLIBC_EXP_TAB;
 static const PowLogRow h_pow_tab[128] = GLIBC_POW_TAB;
+static const LogRow h_logf_tab[16] = GLIBC_LOGF_TAB;
+static const unsigned long long h_expf_tab[32] = GLIBC_EXPF_TAB;
+static const double h_sincosf_tab[28] = GLIBC_SINCOSF_TAB;
+static const LogRow h_powf_tab[16] = GLIBC_POWF_TAB;
+static const double h_powf_poly[5] = GLIBC_POWF_POLY;
+static const double h_exp2f_poly[3] = GLIBC_EXP2F_POLY;
+static const double h_logf_poly[3] = GLIBC_LOGF_POLY;
+static const double h_expf_poly[3] = GLIBC_EXPF_POLY;
 static const double h_pow_poly[7] = GLIBC_POW_POLY;
 static const double h_log_poly[5] = GLIBC_LOG_POLY;
 static const double h_log_poly1[11] = GLIBC_LOG_POLY1;
@@ -106,6 +122,33 @@ GM_FN PowLogRow pow_row(int i) {
   return PowLogRow{__ldg(&g_pow_tab[i].invc), __ldg(&g_pow_tab[i].logc), __ldg(&g_pow_tab[i].logctail)};
 }
 GM_FN double pow_special(double x, double y) { return ::pow(x, y); }
+// single precision: one IEEE float operation each, never contracted
+GM_FN float ff_add(float a, float b) { return __fadd_rn(a, b); }
+GM_FN float ff_sub(float a, float b) { return __fadd_rn(a, -b); }
+GM_FN float ff_mul(float a, float b) { return __fmul_rn(a, b); }
+GM_FN float ff_div(float a, float b) { return __fdiv_rn(a, b); }
+GM_FN uint32_t ff_bits(float x) { return static_cast<uint32_t>(__float_as_int(x)); }
+GM_FN float ff_from_bits(uint32_t u) { return __int_as_float(static_cast<int>(u)); }
+GM_FN double f_f2d(float x) { return static_cast<double>(x); }
+GM_FN float f_d2f(double x) { return __double2float_rn(x); }
+GM_FN LogRow logf_row(int i) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(&g_logf_tab[i]));
+  return LogRow{v.x, v.y};
+}
+GM_FN uint64_t expf_row(int i) { return __ldg(&g_expf_tab[i]); }
+GM_FN float logf_special(float x) { return ::logf(x); }
+GM_FN float expf_special(float x) { return ::expf(x); }
+GM_FN float cosf_large(float x) { return ::cosf(x); }
+GM_FN LogRow powf_row(int i) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(&g_powf_tab[i]));
+  return LogRow{v.x, v.y};
+}
+GM_FN float powf_special(float x, float y) { return ::powf(x, y); }
+#define GM_POWF_POLY c_powf_poly
+#define GM_EXP2F_POLY c_exp2f_poly
+#define GM_SINCOSF c_sincosf_tab
+#define GM_LOGF_POLY c_logf_poly
+#define GM_EXPF_POLY c_expf_poly
 #define GM_POW_POLY c_pow_poly
 #define GM_LOG_POLY c_log_poly
 #define GM_LOG_POLY1 c_log_poly1
@@ -128,6 +171,26 @@ GM_FN void exp_row(int i, uint64_t& tail, uint64_t& sbits) { tail = h_exp_tab[2 
 GM_FN double exp_out_of_range(double x) { return __builtin_exp(x); }
 GM_FN PowLogRow pow_row(int i) { return h_pow_tab[i]; }
 GM_FN double pow_special(double x, double y) { return __builtin_pow(x, y); }
+GM_FN float ff_add(float a, float b) { volatile float r = a + b; return r; }
+GM_FN float ff_sub(float a, float b) { volatile float r = a - b; return r; }
+GM_FN float ff_mul(float a, float b) { volatile float r = a * b; return r; }
+GM_FN float ff_div(float a, float b) { volatile float r = a / b; return r; }
+GM_FN uint32_t ff_bits(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
+GM_FN float ff_from_bits(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
+GM_FN double f_f2d(float x) { return static_cast<double>(x); }
+GM_FN float f_d2f(double x) { volatile float r = static_cast<float>(x); return r; }
+GM_FN LogRow logf_row(int i) { return h_logf_tab[i]; }
+GM_FN uint64_t expf_row(int i) { return h_expf_tab[i]; }
+GM_FN float logf_special(float x) { return __builtin_logf(x); }
+GM_FN float expf_special(float x) { return __builtin_expf(x); }
+GM_FN float cosf_large(float x) { return __builtin_cosf(x); }
+GM_FN LogRow powf_row(int i) { return h_powf_tab[i]; }
+GM_FN float powf_special(float x, float y) { return __builtin_powf(x, y); }
+#define GM_POWF_POLY h_powf_poly
+#define GM_EXP2F_POLY h_exp2f_poly
+#define GM_SINCOSF h_sincosf_tab
+#define GM_LOGF_POLY h_logf_poly
+#define GM_EXPF_POLY h_expf_poly
 #define GM_POW_POLY h_pow_poly
 #define GM_LOG_POLY h_log_poly
 #define GM_LOG_POLY1 h_log_poly1
@@ -630,6 +693,240 @@ GM_FN double cos_medium(double x) {
   // do_sincos(a, da, n + 1)
   const double r = (n & 1) ? do_sin(a, da) : do_cos(a, da);
   return ((n + 1) & 2) ? f_neg(r) : r;
+}
+
+// ============================================================================
+// single precision (real_type = float): logf, expf, cosf, lgammaf
+// ============================================================================
+// e_logf.c / e_expf.c / s_sincosf.h are Szabolcs Nagy's float routines: double
+// arithmetic on the widened argument, one rounding to float at the end (FMA
+// builds, fused operations explicit).  e_lgammaf_r.c is fdlibm's lgamma in float
+// arithmetic (no contraction), with the same structure as lgamma_positive.
+
+// x positive, finite, normal and != 1 handled here; everything else: the platform's logf
+GM_FN float logf(float x) {
+  const uint32_t ix = ff_bits(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) return logf_special(x);
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int i = static_cast<int>((tmp >> 19) & 15u);
+  const int k = static_cast<int32_t>(tmp) >> 23;
+  const double z = f_f2d(ff_from_bits(ix - (tmp & 0xff800000u)));
+  const LogRow row = logf_row(i);
+  const double* A = GM_LOGF_POLY;
+  const double y0 = f_fma(f_i2d(k), GLIBC_LOGF_LN2, row.logc);
+  const double r = f_fma(z, row.invc, -1.0);
+  double y = f_fma(r, A[1], A[2]);
+  const double r2 = f_mul(r, r);
+  const double s = f_add(r, y0);
+  y = f_fma(r2, A[0], y);
+  return f_d2f(f_fma(r2, y, s));
+}
+
+// |x| < 88 here; larger magnitudes and non-finite arguments: the platform's expf
+GM_FN float expf(float x) {
+  const uint32_t abstop = (ff_bits(x) >> 20) & 0x7ffu;
+  if (abstop > 0x42au) return expf_special(x);
+  const double xd = f_f2d(x);
+  const double* C = GM_EXPF_POLY;
+  const double zs = f_fma(GLIBC_EXPF_INVLN2N, xd, GLIBC_EXPF_SHIFT);
+  const uint64_t ki = f_bits(zs);
+  const double kd = f_sub(zs, GLIBC_EXPF_SHIFT);
+  const double r = f_fma(GLIBC_EXPF_INVLN2N, xd, -kd);
+  const double s = f_from_bits(expf_row(static_cast<int>(ki & 31u)) + (ki << 47));
+  const double z = f_fma(r, C[0], C[1]);
+  const double r2 = f_mul(r, r);
+  double y = f_fma(r, C[2], 1.0);
+  y = f_fma(z, r2, y);
+  return f_d2f(f_mul(y, s));
+}
+
+// cos / sin polynomials of s_sincosf.h on a table entry p = {sign[4], hpi_inv, hpi,
+// c0, c1, s1, c2, s2, c3, s3, c4}
+GM_FN float sincosf_poly(double x, double x2, const double* p, int n) {
+  if ((n & 1) == 0) {
+    const double x3 = f_mul(x2, x);
+    const double s1 = f_fma(x2, p[12], p[10]);
+    const double x7 = f_mul(x2, x3);
+    const double s = f_fma(x3, p[8], x);
+    return f_d2f(f_fma(s1, x7, s));
+  }
+  const double x4 = f_mul(x2, x2);
+  const double c1 = f_fma(x2, p[7], p[6]);
+  const double c2 = f_fma(x2, p[13], p[11]);
+  const double x6 = f_mul(x2, x4);
+  const double c = f_fma(x4, p[9], c1);
+  return f_d2f(f_fma(c2, x6, c));
+}
+
+// |x| < 120 here (the Box-Muller angle is below 2 pi); beyond: the platform's cosf
+GM_FN float cosf(float x) {
+  const double* T = GM_SINCOSF;
+  const uint32_t abstop = (ff_bits(x) >> 20) & 0x7ffu;
+  const double y = f_f2d(x);
+  if (abstop <= 0x3f3u) {                       // |x| < pi / 4
+    if (abstop <= 0x397u) return 1.0f;          // |x| < 2^-12
+    return sincosf_poly(y, f_mul(y, y), T, 1);
+  }
+  if (abstop > 0x42eu) return cosf_large(x);
+  const double r = f_mul(y, T[4]);
+  const int n = (static_cast<int>(r) + 0x800000) >> 24;
+  const double xr = f_fma(-f_i2d(n), T[5], y);
+  const double sgn = T[n & 3];
+  const double* p = (n & 2) ? T + 14 : T;
+  const double x2 = f_mul(xr, xr);
+  return sincosf_poly((n & 1) ? f_mul(xr, sgn) : xr, x2, p, n ^ 1);
+}
+
+// e_powf.c: log2(x) in double from a 16-row table and a degree-5 polynomial, y log2(x),
+// exp2 by exp2f's table.  x positive and normal, y finite and non-zero, |y log2 x| < 126
+// here; everything else: the platform's powf.
+GM_FN float powf(float x, float y) {
+  const uint32_t ix = ff_bits(x), iy = ff_bits(y);
+  if (ix - 0x00800000u > 0x7effffffu || 2u * iy - 1u > 0xfefffffeu) return powf_special(x, y);
+  const double* A = GM_POWF_POLY;
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int i = static_cast<int>((tmp >> 19) & 15u);
+  const uint32_t top = tmp & 0xff800000u;
+  const int k = static_cast<int32_t>(top) >> 23;
+  const double z = f_f2d(ff_from_bits(ix - top));
+  const LogRow row = powf_row(i);
+  const double r = f_fma(z, row.invc, -1.0);
+  const double y0 = f_add(f_i2d(k), row.logc);
+  double ya = f_fma(r, A[0], A[1]);
+  const double p = f_fma(r, A[2], A[3]);
+  const double r2 = f_mul(r, r);
+  double q = f_fma(r, A[4], y0);
+  const double r4 = f_mul(r2, r2);
+  q = f_fma(r2, p, q);
+  ya = f_fma(ya, r4, q);
+  const double ylogx = f_mul(f_f2d(y), ya);
+  if (((f_bits(ylogx) >> 47) & 0xffffu) > 0x80beu) return powf_special(x, y);      // |y log2 x| >= 126 (scaled) or negative large
+  const double* C = GM_EXP2F_POLY;
+  const double kd0 = f_add(ylogx, GLIBC_EXP2F_SHIFT_SCALED);
+  const uint64_t ki = f_bits(kd0);
+  const double kd = f_sub(kd0, GLIBC_EXP2F_SHIFT_SCALED);
+  const double rr = f_sub(ylogx, kd);
+  const double s = f_from_bits(expf_row(static_cast<int>(ki & 31u)) + (ki << 47));
+  const double zz = f_fma(rr, C[0], C[1]);
+  const double rr2 = f_mul(rr, rr);
+  double yy = f_fma(rr, C[2], 1.0);
+  yy = f_fma(zz, rr2, yy);
+  return f_d2f(f_mul(yy, s));
+}
+
+GM_FN float lgammaf_2_to_8(float x) {
+  const int i = static_cast<int>(x);
+  const float y = ff_sub(x, static_cast<float>(i));
+  float p = ff_add(GLIBC_LGF_S5, ff_mul(y, GLIBC_LGF_S6));
+  p = ff_add(GLIBC_LGF_S4, ff_mul(y, p));
+  p = ff_add(GLIBC_LGF_S3, ff_mul(y, p));
+  p = ff_add(GLIBC_LGF_S2, ff_mul(y, p));
+  p = ff_add(GLIBC_LGF_S1, ff_mul(y, p));
+  p = ff_add(GLIBC_LGF_S0, ff_mul(y, p));
+  p = ff_mul(y, p);
+  float q = ff_add(GLIBC_LGF_R5, ff_mul(y, GLIBC_LGF_R6));
+  q = ff_add(GLIBC_LGF_R4, ff_mul(y, q));
+  q = ff_add(GLIBC_LGF_R3, ff_mul(y, q));
+  q = ff_add(GLIBC_LGF_R2, ff_mul(y, q));
+  q = ff_add(GLIBC_LGF_R1, ff_mul(y, q));
+  q = ff_add(1.0f, ff_mul(y, q));
+  float r = ff_add(ff_mul(0.5f, y), ff_div(p, q));
+  if (i >= 3) {
+    float z = 1.0f;
+    if (i >= 7) z = ff_mul(z, ff_add(y, 6.0f));
+    if (i >= 6) z = ff_mul(z, ff_add(y, 5.0f));
+    if (i >= 5) z = ff_mul(z, ff_add(y, 4.0f));
+    if (i >= 4) z = ff_mul(z, ff_add(y, 3.0f));
+    z = ff_mul(z, ff_add(y, 2.0f));
+    r = ff_add(r, logf(z));
+  }
+  return r;
+}
+
+// x positive and finite (e_lgammaf_r.c; the thresholds are the float images of
+// lgamma_positive's)
+GM_FN float lgammaf_positive(float x) {
+  const uint32_t ix = ff_bits(x);
+  if (ix < 0x30800000u) return -logf(x);                       // x < 2^-30
+  if (ix == 0x3f800000u || ix == 0x40000000u) return 0.0f;     // 1 and 2
+  float r;
+  if (ix < 0x40000000u) {                                      // x < 2
+    float y;
+    int i;
+    if (ix <= 0x3f666666u) {
+      r = -logf(x);
+      if (ix >= 0x3f3b4a20u) { y = ff_sub(1.0f, x); i = 0; }
+      else if (ix >= 0x3e6d3308u) { y = ff_sub(x, GLIBC_LGF_TC_M1); i = 1; }
+      else { y = x; i = 2; }
+    } else {
+      r = 0.0f;
+      if (ix >= 0x3fdda618u) { y = ff_sub(2.0f, x); i = 0; }
+      else if (ix >= 0x3f9da620u) { y = ff_sub(x, GLIBC_LGF_TC); i = 1; }
+      else { y = ff_sub(x, 1.0f); i = 2; }
+    }
+    if (i == 0) {
+      const float z = ff_mul(y, y);
+      float p1 = ff_add(GLIBC_LGF_A8, ff_mul(z, GLIBC_LGF_A10));
+      p1 = ff_add(GLIBC_LGF_A6, ff_mul(z, p1));
+      p1 = ff_add(GLIBC_LGF_A4, ff_mul(z, p1));
+      p1 = ff_add(GLIBC_LGF_A2, ff_mul(z, p1));
+      p1 = ff_add(GLIBC_LGF_A0, ff_mul(z, p1));
+      float p2 = ff_add(GLIBC_LGF_A9, ff_mul(z, GLIBC_LGF_A11));
+      p2 = ff_add(GLIBC_LGF_A7, ff_mul(z, p2));
+      p2 = ff_add(GLIBC_LGF_A5, ff_mul(z, p2));
+      p2 = ff_add(GLIBC_LGF_A3, ff_mul(z, p2));
+      p2 = ff_add(GLIBC_LGF_A1, ff_mul(z, p2));
+      p2 = ff_mul(z, p2);
+      const float p = ff_add(ff_mul(y, p1), p2);
+      r = ff_add(r, ff_sub(p, ff_mul(0.5f, y)));
+    } else if (i == 1) {
+      const float z = ff_mul(y, y);
+      const float w = ff_mul(z, y);
+      float p1 = ff_add(GLIBC_LGF_T9, ff_mul(w, GLIBC_LGF_T12));
+      p1 = ff_add(GLIBC_LGF_T6, ff_mul(w, p1));
+      p1 = ff_add(GLIBC_LGF_T3, ff_mul(w, p1));
+      p1 = ff_add(GLIBC_LGF_T0, ff_mul(w, p1));
+      float p2 = ff_add(GLIBC_LGF_T10, ff_mul(w, GLIBC_LGF_T13));
+      p2 = ff_add(GLIBC_LGF_T7, ff_mul(w, p2));
+      p2 = ff_add(GLIBC_LGF_T4, ff_mul(w, p2));
+      p2 = ff_add(GLIBC_LGF_T1, ff_mul(w, p2));
+      float p3 = ff_add(GLIBC_LGF_T11, ff_mul(w, GLIBC_LGF_T14));
+      p3 = ff_add(GLIBC_LGF_T8, ff_mul(w, p3));
+      p3 = ff_add(GLIBC_LGF_T5, ff_mul(w, p3));
+      p3 = ff_add(GLIBC_LGF_T2, ff_mul(w, p3));
+      const float p = ff_sub(ff_mul(z, p1), ff_sub(GLIBC_LGF_TT, ff_mul(w, ff_add(p2, ff_mul(y, p3)))));
+      r = ff_add(r, ff_add(GLIBC_LGF_TF, p));
+    } else {
+      float p1 = ff_add(GLIBC_LGF_U4, ff_mul(y, GLIBC_LGF_U5));
+      p1 = ff_add(GLIBC_LGF_U3, ff_mul(y, p1));
+      p1 = ff_add(GLIBC_LGF_U2, ff_mul(y, p1));
+      p1 = ff_add(GLIBC_LGF_U1, ff_mul(y, p1));
+      p1 = ff_add(GLIBC_LGF_U0, ff_mul(y, p1));
+      p1 = ff_mul(y, p1);
+      float p2 = ff_add(GLIBC_LGF_V4, ff_mul(y, GLIBC_LGF_V5));
+      p2 = ff_add(GLIBC_LGF_V3, ff_mul(y, p2));
+      p2 = ff_add(GLIBC_LGF_V2, ff_mul(y, p2));
+      p2 = ff_add(GLIBC_LGF_V1, ff_mul(y, p2));
+      p2 = ff_add(1.0f, ff_mul(y, p2));
+      r = ff_add(r, ff_add(ff_mul(-0.5f, y), ff_div(p1, p2)));
+    }
+    return r;
+  }
+  if (ix < 0x41000000u) return lgammaf_2_to_8(x);               // 2 <= x < 8
+  if (ix < 0x5c800000u) {                                      // 8 <= x < 2^58
+    const float t = logf(x);
+    const float z = ff_div(1.0f, x);
+    const float y = ff_mul(z, z);
+    float w = ff_add(GLIBC_LGF_W5, ff_mul(y, GLIBC_LGF_W6));
+    w = ff_add(GLIBC_LGF_W4, ff_mul(y, w));
+    w = ff_add(GLIBC_LGF_W3, ff_mul(y, w));
+    w = ff_add(GLIBC_LGF_W2, ff_mul(y, w));
+    w = ff_add(GLIBC_LGF_W1, ff_mul(y, w));
+    w = ff_add(GLIBC_LGF_W0, ff_mul(z, w));
+    return ff_add(ff_mul(ff_sub(x, 0.5f), ff_sub(t, 1.0f)), w);
+  }
+  return ff_mul(x, ff_sub(logf(x), 1.0f));                     // 2^58 <= x
 }
 
 // ---- the same function for lock-step execution ---------------------------------

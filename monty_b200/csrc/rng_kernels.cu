@@ -207,14 +207,14 @@ cudaError_t launch_xoshiro_run(int gen, uint64_t seed, int n, uint64_t* values_d
 }
 
 // The lgamma-of-small-integers table behind m_lgamma (samplers.cuh): entry i is
-// what m_lgamma(i) computes without the table -- glibc's lgamma bit for bit in
-// double (glibc_math.cuh), the toolkit's lgammaf in float -- so a table hit is
+// what m_lgamma(i) computes without the table -- glibc's lgamma / lgammaf bit for
+// bit (glibc_math.cuh) -- so a table hit is
 // bit-identical to the call it replaces.
 __global__ void lgt_build_kernel(double* __restrict__ d, float* __restrict__ f, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     d[i] = i >= 1 ? glibc::lgamma_positive(static_cast<double>(i)) : lgamma(static_cast<double>(i));
-    f[i] = lgammaf(static_cast<float>(i));
+    f[i] = i >= 1 ? glibc::lgammaf_positive(static_cast<float>(i)) : lgammaf(static_cast<float>(i));
   }
 }
 cudaError_t launch_lgamma_table_build(double* d, float* f, int n, cudaStream_t st) {

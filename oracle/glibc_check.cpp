@@ -126,6 +126,62 @@ extern "C" int64_t gm_compare_lgamma_batch(uint64_t seed, int64_t n) {
   }
   return mism;
 }
+// The float routines, EXHAUSTIVELY: every float bit pattern in [lo_bits, hi_bits) through
+// fn 0 = logf, 1 = expf, 2 = cosf, 3 = lgammaf (positive finite arguments only) against the
+// live libm; returns the number of differing results, *bad = the first offender's bits.
+extern "C" int64_t gm_compare_float(int fn, uint32_t lo_bits, uint32_t hi_bits, uint32_t* bad) {
+  int64_t mism = 0;
+  uint32_t first = 0;
+#pragma omp parallel for reduction(+ : mism) schedule(static)
+  for (int64_t u = lo_bits; u < static_cast<int64_t>(hi_bits); ++u) {
+    float x, got, want;
+    const uint32_t b = static_cast<uint32_t>(u);
+    std::memcpy(&x, &b, 4);
+    int sg = 0;
+    switch (fn) {
+      case 0: got = mb200::glibc::logf(x); want = ::logf(x); break;
+      case 1: got = mb200::glibc::expf(x); want = ::expf(x); break;
+      case 2: got = mb200::glibc::cosf(x); want = ::cosf(x); break;
+      default: got = mb200::glibc::lgammaf_positive(x); want = ::lgammaf_r(x, &sg); break;
+    }
+    uint32_t gb, wb;
+    std::memcpy(&gb, &got, 4); std::memcpy(&wb, &want, 4);
+    if (gb != wb && !(got != got && want != want)) {
+      ++mism;
+#pragma omp critical
+      if (first == 0) first = b;
+    }
+  }
+  if (bad) *bad = first;
+  return mism;
+}
+// powf(x, y) for n pseudo-random pairs: x a uniform float in (0, 1] or any positive float,
+// y in (0.05, 20) or any float
+extern "C" int64_t gm_compare_powf(uint64_t seed, int64_t n, int mode) {
+  int64_t mism = 0;
+#pragma omp parallel for reduction(+ : mism) schedule(static)
+  for (int64_t c = 0; c < (n + 65535) / 65536; ++c) {
+    uint64_t s = seed + 0x1234567ull * static_cast<uint64_t>(c);
+    for (int j = 0; j < 65536; ++j) {
+      const uint64_t w = splitmix(s);
+      float x, y;
+      uint32_t xb = static_cast<uint32_t>(w), yb = static_cast<uint32_t>(w >> 32);
+      if (mode == 0) {
+        x = static_cast<float>(xb >> 8) * 0x1p-24f + 0x1p-25f;
+        y = 0.05f + 20.0f * (static_cast<float>(yb >> 8) * 0x1p-24f);
+      } else {
+        xb &= 0x7fffffffu;
+        std::memcpy(&x, &xb, 4);
+        std::memcpy(&y, &yb, 4);
+      }
+      const float got = mb200::glibc::powf(x, y), want = ::powf(x, y);
+      uint32_t gb, wb;
+      std::memcpy(&gb, &got, 4); std::memcpy(&wb, &want, 4);
+      mism += gb != wb && !(got != got && want != want);
+    }
+  }
+  return mism;
+}
 extern "C" double gm_pow(double x, double y) { return mb200::glibc::pow(x, y); }
 extern "C" double gm_exp(double x) { return mb200::glibc::exp(x); }
 extern "C" double gm_lgamma(double x) { return mb200::glibc::lgamma_positive(x); }

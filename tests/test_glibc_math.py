@@ -22,6 +22,18 @@ LIB = os.path.join(ROOT, "oracle", "libglibc_check.so")
 N = int(os.environ.get("MONTY_B200_GLIBC_N", "20000000"))
 
 KINDS = {
+    9: "lgamma on (0, 10): every piece below 8",
+    10: "lgamma of any positive normal double",
+    11: "lgamma on (0.5, 300.5): the densities' range",
+    12: "lgamma of integers and half-integers",
+    13: "exp on [-700, 700]",
+    14: "exp of every magnitude below 2",
+    15: "pow(uniform, (0.05, 12)): the gamma / Weibull samplers' calls",
+    16: "pow(any positive normal, (-20, 20))",
+    17: "pow((0, 50), any bit pattern)",
+    6: "cos (lock-step formulation) of the Box-Muller angle",
+    7: "cos (lock-step formulation) on [-1000, 1000]",
+    8: "cos (lock-step formulation), magnitudes to 1e8",
     0: "log of random_real() outputs",
     1: "log of random positive normal doubles",
     2: "log on [0.9, 1.1] (the window around 1 and its edges)",
@@ -41,6 +53,14 @@ def gm():
     for f in (lib.gm_log, lib.gm_cos):
         f.restype = ctypes.c_double
         f.argtypes = [ctypes.c_double]
+    lib.gm_compare_float.restype = ctypes.c_int64
+    lib.gm_compare_float.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
+    lib.gm_compare_powf.restype = ctypes.c_int64
+    lib.gm_compare_powf.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int]
+    lib.gm_compare_log_batch.restype = ctypes.c_int64
+    lib.gm_compare_log_batch.argtypes = [ctypes.c_uint64, ctypes.c_int64]
+    lib.gm_compare_lgamma_batch.restype = ctypes.c_int64
+    lib.gm_compare_lgamma_batch.argtypes = [ctypes.c_uint64, ctypes.c_int64]
     return lib
 
 
@@ -49,6 +69,33 @@ def test_same_bits_as_libm(gm, kind):
     bad = ctypes.c_double(0)
     mism = gm.gm_compare(kind, 20240607 + kind, N, ctypes.byref(bad))
     assert mism == 0, "%s: %d of %d differ, first at x = %s" % (KINDS[kind], mism, N, bad.value.hex())
+
+
+# every 16th float bit pattern by default (the whole set takes ~40 s on 8 cores:
+# MONTY_B200_GLIBC_FLOAT_STRIDE=1); the committed result of the exhaustive run is 0 / 0 / 0 / 0
+FLOAT_STRIDE = int(os.environ.get("MONTY_B200_GLIBC_FLOAT_STRIDE", "16"))
+
+
+@pytest.mark.parametrize("fn,name,lo,hi", [(0, "logf", 0, 0xFFFFFFFF), (1, "expf", 0, 0xFFFFFFFF),
+                                          (2, "cosf", 0, 0xFF800000), (3, "lgammaf", 1, 0x7F800000)])
+def test_float_routines_same_bits_as_libm(gm, fn, name, lo, hi):
+    """real_type = float: logf / expf / cosf / lgammaf over the float bit patterns
+    (blocks of 2^20 patterns, every FLOAT_STRIDE-th block)."""
+    bad = ctypes.c_uint32(0)
+    block = 1 << 20
+    total = 0
+    for k, start in enumerate(range(lo, hi, block)):
+        if k % FLOAT_STRIDE:
+            continue
+        total += gm.gm_compare_float(fn, start, min(hi, start + block), ctypes.byref(bad))
+    assert total == 0, "%s: %d differ, first bits 0x%08x" % (name, total, bad.value)
+
+
+def test_powf_and_the_batched_forms(gm):
+    assert gm.gm_compare_powf(5, N, 0) == 0          # powf(uniform float, (0.05, 20))
+    assert gm.gm_compare_powf(6, N, 1) == 0          # powf(any positive float, any float)
+    assert gm.gm_compare_log_batch(7, N // 4) == 0   # log_positive_normal_batch<4> == four calls
+    assert gm.gm_compare_lgamma_batch(3, N // 6) == 0
 
 
 def test_the_comparison_can_fail(gm):

@@ -13,13 +13,12 @@ Bars (BASELINE.json north_star):
     BIT-IDENTICAL, shifted and scaled parameters included; cauchy (tan: the
     toolkit's routine, <= 2 ulp) is held to 4 eps of the terms `location + scale *
     tan` adds;
-  * float real_type: continuous draws within 1e-6 relative on standard
-    parameters.  Integer-valued float draws that go through lgammaf / logf
-    with cancellation (Poisson lambda >~ 1e3, hypergeometric H2PE, negative
-    binomial) depend on the last bit of the platform's float libm in the
-    REFERENCE ITSELF (glibc lgammaf differs from the correctly rounded value
-    for 36% of arguments); for those the measured mismatch fraction is bounded
-    and reported, and the distribution is checked statistically instead.
+  * float real_type: bit-identical too (the north-star asks for 1e-6 relative):
+    glibc's logf / expf / powf / cosf / lgammaf are restated bit for bit, which
+    also makes the integer-valued float draws that subtract large lgammaf terms
+    (Poisson lambda >~ 1e3, hypergeometric H2PE, negative binomial) exact --
+    they depend on the last bit of the platform's float libm in the REFERENCE
+    ITSELF; cauchy (tanf) is the one sampler held to 1e-6 relative.
 """
 import numpy as np
 import pytest
@@ -151,49 +150,28 @@ def test_double_continuous_within_4_ulp(mb, oracle, name):
         assert d.max() == 0, (name, d.max())       # shapes >= 2 here: no pow
 
 
-@pytest.mark.parametrize("name", ["real", "uniform", "binomial", "beta_binomial_ab", "zi_poisson",
-                                  "zi_negative_binomial_prob", "zi_negative_binomial_mu",
-                                  "beta_binomial_prob"])
-def test_float_exact_samplers(mb, oracle, name):
-    n, ns = 2048, 16
+@pytest.mark.parametrize("name", ALL)
+def test_float_real_type_is_bit_identical(mb, oracle, name):
+    """real_type = float (the reference's `<float>` instantiations, what dust2 /
+    odin2 models compiled for single precision call): logf, expf, powf, cosf and
+    lgammaf return glibc's bits on the device (detail/glibc_math.cuh: every float
+    checked against the host libm, exhaustively, in tests/test_glibc_math.py), so
+    every sampler is bit-identical -- draws AND final states, the integer-valued
+    ones whose accept tests subtract large lgammaf terms included (round 1: 0.5-3%
+    of those draws differed).  Only cauchy (tanf: the toolkit's) is held to 1e-6
+    relative instead."""
+    n, ns = 8192, 32
     pars = sampler_cases(n)[name]
     y, st, _ = gpu_sample(mb, name, n, ns, pars, rt="f32")
     ost = oracle.seed_states(7, n)
     exp = oracle.sample(name, ost, ns, pars, "f32")
-    assert np.mean(y != exp) <= 1e-4, np.mean(y != exp)
-    assert np.mean((st != ost).any(axis=1)) <= 1e-3
-
-
-@pytest.mark.parametrize("name", sorted(standard_cases(4)))
-def test_float_continuous_within_1e6_relative(mb, oracle, name):
-    n, ns = 2048, 32
-    pars = standard_cases(n)[name]
-    y, st, _ = gpu_sample(mb, name, n, ns, pars, rt="f32")
-    ost = oracle.seed_states(7, n)
-    exp = oracle.sample(name, ost, ns, pars, "f32")
-    same_stream = (st == ost).all(axis=1)
-    assert same_stream.mean() > 0.995          # a float accept/reject flip desynchronises a stream
-    rel = np.abs(y - exp)[same_stream] / np.maximum(np.abs(exp[same_stream]), 1e-30)
-    # cancellation near zero of cos / tan amplifies the 1-ulp differences of the
-    # float libm; 1e-6 holds for all but a vanishing fraction
-    assert np.mean(rel <= 1e-6) > 0.998, (name, np.mean(rel <= 1e-6))
-    assert np.median(rel) <= 1.2e-7
-
-
-@pytest.mark.parametrize("name,limit", [("poisson", 2e-2), ("negative_binomial_prob", 5e-3),
-                                        ("hypergeometric", 3e-2)])
-def test_float_libm_sensitive_samplers_are_bounded(mb, oracle, name, limit):
-    """See the module docstring: reported, bounded, and statistically checked
-    in test_gpu_statistics.py."""
-    n, ns = 4096, 16
-    pars = sampler_cases(n)[name]
-    y, st, _ = gpu_sample(mb, name, n, ns, pars, rt="f32")
-    ost = oracle.seed_states(7, n)
-    exp = oracle.sample(name, ost, ns, pars, "f32")
-    frac = np.mean(y != exp)
-    print("float %s: mismatch fraction %.3g, diverged streams %.3g"
-          % (name, frac, np.mean((st != ost).any(axis=1))))
-    assert frac <= limit
+    assert np.array_equal(st, ost), "%d streams ended in a different state" % int((st != ost).any(axis=1).sum())
+    if name == "cauchy":
+        loc = np.abs(np.broadcast_to(np.atleast_1d(pars[0]), (n,)))[:, None]
+        assert (np.abs(y - exp) <= 1e-6 * (np.abs(exp) + loc)).all()
+    else:
+        same = (y == exp) | (np.isnan(y) & np.isnan(exp))
+        assert same.all(), (name, float(1 - same.mean()), y[~same][:3], exp[~same][:3])
 
 
 def test_empty_requests(mb):

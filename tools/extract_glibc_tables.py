@@ -22,6 +22,8 @@ Tables:
     scalar constants of s_sin.c / branred (big, hp0, hp1, mp1, mp2, pp3, pp4,
     hpinv, toint, sn3, sn5, cs2, cs4, cs6, s1..s5) -- written from their
     published values and CHECKED to be present in the library's .rodata.
+    __logf_data, __exp2f_data, __sincosf_table, e_lgammaf_r.c's pool: the float
+                    routines behind real_type = float
     __pow_log_data  poly[7], tab[128] {invc, logc, logctail} of pow's own log
     __exp_data      invln2N, shift, -ln2/N (hi, lo), C2..C5, tab[128] {tail, scale}
     e_lgamma_r.c    the 65 polynomial coefficients of fdlibm's lgamma (a, t, u, v,
@@ -192,6 +194,61 @@ def main(out=None):
     for k in range(128):
         invc, pad, logc, tail = powtab[4 * k:4 * k + 4]
         assert pad == 0.0 and 0.7 < invc < 1.45 and abs(logc + tail - math.log(1 / invc)) < 1e-15, k
+    # ---- float routines (real_type = float): e_logf.c, e_expf.c, s_sincosf.h (Szabolcs
+    # Nagy; double arithmetic inside), e_lgammaf_r.c (fdlibm, float arithmetic)
+    lf = find_doubles(blob, off, size, [float.fromhex("0x1.62e42fefa39efp-1"), float.fromhex("-0x1.00ea348b88334p-2")])
+    if lf < 0:
+        raise SystemExit("logf data signature not found")
+    LOGF = dict(ln2=dbl(blob, lf, 1)[0], poly=dbl(blob, lf + 8, 3), tab=dbl(blob, lf - 256, 32))
+    for k in range(16):
+        assert abs(LOGF["tab"][2 * k + 1] - math.log(1 / LOGF["tab"][2 * k])) < 1e-15, k
+    ef = find_doubles(blob, off, size, [float.fromhex("0x1.8p52"), float.fromhex("0x1.71547652b82fep+5")])
+    if ef < 0:
+        raise SystemExit("expf data signature not found")
+    EXPF = dict(shift=dbl(blob, ef, 1)[0], invln2n=dbl(blob, ef + 8, 1)[0], poly=dbl(blob, ef + 16, 3),
+                tab=list(struct.unpack_from("<32Q", blob, ef - 0x120)))
+    for k in range(32):
+        sc = struct.unpack("<d", struct.pack("<Q", EXPF["tab"][k] + (k << 47)))[0]
+        assert abs(sc - 2.0 ** (k / 32)) < 1e-15, k
+    sf = find_doubles(blob, off, size, [float.fromhex("0x1.45f306dc9c883p+23"), float.fromhex("0x1.921fb54442d18p+0")])
+    if sf < 0:
+        raise SystemExit("sincosf table signature not found")
+    SINCOSF = dbl(blob, sf - 0x20, 28)          # two entries: {sign[4], hpi_inv, hpi, c0, c1, s1, c2, s2, c3, s3, c4}
+    assert SINCOSF[:4] == [1.0, -1.0, -1.0, 1.0] and SINCOSF[6] == 1.0 and SINCOSF[14 + 6] == -1.0
+    # __powf_log2_data {tab[16] {invc, logc}, poly[5]} anchored on the published polynomial;
+    # powf's exp2 half uses __exp2f_data.tab with shift_scaled and poly[3] (the words before `shift`)
+    pf = find_doubles(blob, off, size, [float.fromhex("0x1.27616c9496e0bp-2"), float.fromhex("-0x1.71969a075c67ap-2")])
+    if pf < 0:
+        raise SystemExit("powf log2 data signature not found")
+    POWF = dict(poly=dbl(blob, pf, 5), tab=dbl(blob, pf - 256, 32), shift_scaled=dbl(blob, ef - 0x20, 1)[0],
+                exp2_poly=dbl(blob, ef - 0x18, 3))
+    for k in range(16):
+        assert abs(POWF["tab"][2 * k + 1] - math.log2(1 / POWF["tab"][2 * k])) < 1e-15, k
+    assert POWF["shift_scaled"] == float.fromhex("0x1.8p47") and abs(POWF["exp2_poly"][2] - math.log(2)) < 1e-9
+    a2f, a0f = struct.unpack("<f", struct.pack("<f", 0.0673523023724556))[0], struct.unpack("<f", struct.pack("<f", 0.07721566408872604))[0]
+    pat = struct.pack("<2f", a2f, a0f)
+    gf = blob.find(pat, off, off + size)
+    if gf < 0:
+        raise SystemExit("lgammaf constant pool not found")
+    gf += 4                                         # file offset of a0 (float)
+    def atf(idx):
+        return struct.unpack_from("<f", blob, gf + 4 * idx)[0]
+    LGF = {}
+    for name, idx, neg in (("a0", 0, 0), ("a1", 6, 0), ("a2", -1, 0), ("a3", 5, 0), ("a4", -2, 0), ("a5", 4, 0), ("a6", -3, 0),
+                           ("a7", 3, 0), ("a8", -4, 0), ("a9", 2, 0), ("a10", -5, 0), ("a11", 1, 0), ("tc", -6, 0), ("tc_m1", -7, 0),
+                           ("t12", 7, 0), ("t9", 8, 1), ("t6", 9, 0), ("t3", 10, 1), ("t0", 11, 0),
+                           ("t14", 12, 0), ("t11", 13, 1), ("t8", 14, 0), ("t5", 15, 1), ("t2", 16, 0),
+                           ("t13", 17, 0), ("t10", 18, 0), ("t7", 19, 1), ("t4", 20, 0), ("t1", 21, 1), ("tt", 22, 0), ("tf", 23, 1),
+                           ("u5", 24, 0), ("u4", 25, 0), ("u3", 26, 0), ("u2", 27, 0), ("u1", 28, 0),
+                           ("v5", 29, 0), ("v4", 30, 0), ("v3", 31, 0), ("v2", 32, 0), ("v1", 33, 0),
+                           ("s6", 34, 0), ("s5", 35, 0), ("s4", 36, 0), ("s3", 37, 0), ("s2", 38, 0), ("s1", 39, 0),
+                           ("r6", 40, 0), ("r5", 41, 0), ("r4", 42, 0), ("r3", 43, 0), ("r2", 44, 0), ("r1", 45, 0),
+                           ("w6", 46, 0), ("w5", 47, 0), ("w4", 48, 1), ("w3", 49, 0), ("w2", 50, 1), ("w1", 51, 0), ("w0", 52, 0)):
+        LGF[name] = -atf(idx) if neg else atf(idx)
+    LGF["u0"] = -LGF["a0"]
+    LGF["s0"] = -LGF["a0"]
+    assert abs(LGF["tc"] - 1.46163214) < 1e-6 and abs(LGF["w0"] - 0.41893853) < 1e-6 and abs(LGF["w1"] - 1 / 12) < 1e-6
+    assert LGF["w6"] < 0 and LGF["t13"] < 0 and abs(LGF["r1"] - 1.3920053) < 1e-6 and abs(LGF["u1"] - 0.63282706) < 1e-6
     if out is None:
         return dict(ln2hi=ln2hi, lgamma=LG, ln2lo=ln2lo, A=A, B=B, T=T, sincos=sct, missing=missing,
                     log_addr=addr + (log_off - off), sincos_addr=addr + (j - off))
@@ -243,6 +300,26 @@ def main(out=None):
     for k in range(128):
         L.append("  {%s, %s, %s}, \\" % (fh(powtab[4 * k]), fh(powtab[4 * k + 2]), fh(powtab[4 * k + 3])))
     L[-1] = L[-1][:-3] + " }"
+    fhf = lambda v: float(v).hex() + "f"  # noqa: E731  (exact: a float widened to double prints exactly)
+    L.append("/* __logf_data: tab[16] = {invc, logc}, ln2, poly[3] (double arithmetic) */")
+    L.append("#define GLIBC_LOGF_LN2 %s" % fh(LOGF["ln2"]))
+    L.append("#define GLIBC_LOGF_POLY { %s }" % ", ".join(fh(v) for v in LOGF["poly"]))
+    L.append("#define GLIBC_LOGF_TAB { %s }" % ", ".join("{%s, %s}" % (fh(LOGF["tab"][2 * k]), fh(LOGF["tab"][2 * k + 1])) for k in range(16)))
+    L.append("/* __exp2f_data as expf uses it: tab[32] (scale bits - (i << 47)), shift, invln2 * 32, poly_scaled[3] */")
+    L.append("#define GLIBC_EXPF_SHIFT %s" % fh(EXPF["shift"]))
+    L.append("#define GLIBC_EXPF_INVLN2N %s" % fh(EXPF["invln2n"]))
+    L.append("#define GLIBC_EXPF_POLY { %s }" % ", ".join(fh(v) for v in EXPF["poly"]))
+    L.append("#define GLIBC_EXPF_TAB { %s }" % ", ".join("0x%016xull" % v for v in EXPF["tab"]))
+    L.append("/* powf: __powf_log2_data {tab[16] {invc, log2 c}, poly[5]}, exp2f's shift_scaled and poly[3] */")
+    L.append("#define GLIBC_POWF_POLY { %s }" % ", ".join(fh(v) for v in POWF["poly"]))
+    L.append("#define GLIBC_POWF_TAB { %s }" % ", ".join("{%s, %s}" % (fh(POWF["tab"][2 * k]), fh(POWF["tab"][2 * k + 1])) for k in range(16)))
+    L.append("#define GLIBC_EXP2F_SHIFT_SCALED %s" % fh(POWF["shift_scaled"]))
+    L.append("#define GLIBC_EXP2F_POLY { %s }" % ", ".join(fh(v) for v in POWF["exp2_poly"]))
+    L.append("/* __sincosf_table[2]: {sign[4], hpi_inv, hpi, c0, c1, s1, c2, s2, c3, s3, c4} */")
+    L.append("#define GLIBC_SINCOSF_TAB { %s }" % ", ".join(fh(v) for v in SINCOSF))
+    L.append("/* e_lgammaf_r.c (fdlibm, float) constants, signs as published */")
+    for name in sorted(LGF, key=lambda n: (n.rstrip("0123456789_m"), int("".join(c for c in n if c.isdigit()) or 0))):
+        L.append("#define GLIBC_LGF_%s %s" % (name.upper(), fhf(LGF[name])))
     L.append("/* e_lgamma_r.c (fdlibm) constants, signs as published */")
     for name in sorted(LG, key=lambda n: (n.rstrip("0123456789_m"), int("".join(c for c in n if c.isdigit()) or 0))):
         L.append("#define GLIBC_LG_%s %s" % (name.upper(), fh(LG[name])))
