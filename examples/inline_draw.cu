@@ -174,6 +174,10 @@ __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* 
     case 6: r = mb200::m_lgamma(v); break;
     case 7: r = mb200::m_exp(v); break;
     case 8: r = mb200::m_pow(v, x[i ^ 1]); break;        // exponent: the neighbouring element
+    case 9: r = mb200::m_tan(v); break;
+    case 10: r = mb200::m_log1p(v); break;
+    case 11: r = mb200::m_erfc(v); break;
+    case 12: r = static_cast<double>(mb200::m_tan(static_cast<float>(v))); break;
     default: r = 0.0; break;
   }
   y[i] = r;
@@ -181,7 +185,7 @@ __global__ void math_probe_kernel(int fn, const double* __restrict__ x, double* 
 }  // namespace
 
 extern "C" int mb200_example_math_probe(int fn, const double* x_host, double* y_host, size_t n) {
-  if (!x_host || !y_host || fn < 0 || fn > 8) return MB200_ERR_ARG;
+  if (!x_host || !y_host || fn < 0 || fn > 12) return MB200_ERR_ARG;
   double *dx = nullptr, *dy = nullptr;
   int rc = MB200_OK;
   if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&dy, n * sizeof(double)) != cudaSuccess ||

@@ -10,7 +10,9 @@
 
 namespace mb200 {
 
-__device__ __forceinline__ double m_log1p(double x) { return log1p(x); }
+// log1p, erfc: glibc's s_log1p.c / s_erf.c bit for bit (glibc_math.cuh)
+__device__ __forceinline__ double m_log1p(double x) { return glibc::log1p(x); }
+__device__ __forceinline__ double m_erfc(double x) { return glibc::erfc(x); }
 __device__ __forceinline__ float m_log1p(float x) { return log1pf(x); }
 
 template <typename T> __device__ __forceinline__ T maybe_log(T x, bool lg) {   // :33-36
@@ -152,8 +154,8 @@ template <typename T> __device__ T dens_truncated_normal(T x, T mu, T sd, T min,
     const T y_min = (min - mu) / sd;
     const T y_max = (max - mu) / sd;
     // -y / M_SQRT2 is a double whatever T is: std::erfc(double)
-    const double z_min = 0.5 * erfc(-y_min / 1.41421356237309504880);
-    const double z_max = 0.5 * erfc(-y_max / 1.41421356237309504880);
+    const double z_min = 0.5 * m_erfc(-y_min / 1.41421356237309504880);
+    const double z_max = 0.5 * m_erfc(-y_max / 1.41421356237309504880);
     const double z = z_max - z_min;
     ret = d - m_log(z);
   }
@@ -163,7 +165,10 @@ template <typename T> __device__ T dens_cauchy(T x, T location, T scale, bool lg
   // monty::math::log(M_PI) is the double log, so the sum is a double and
   // maybe_log<double> is what gets deduced
   const T q = (x - location) / scale;
-  const T q2 = sizeof(T) == 4 ? static_cast<T>(m_pow(static_cast<double>(q), 2.0)) : static_cast<T>(m_pow(static_cast<double>(q), 2.0));
+  // std::pow(q, 2): the host compiler folds a square into one multiplication (GCC does so at
+  // every optimisation level above -O0, with or without -ffast-math), which is what the
+  // compiled reference executes; libm's pow(q, 2.0) can differ from q * q in the last bit
+  const T q2 = q * q;
   const double ret = -m_log(M_PI) - m_log(scale) - m_log1p(q2);
   return lg ? static_cast<T>(ret) : static_cast<T>(m_exp(ret));
 }

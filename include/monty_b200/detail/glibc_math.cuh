@@ -50,6 +50,7 @@ struct alignas(16) LogRow { double invc, logc; };
 struct SinCosRow { double sn, ssn, cs, ccs; };
 struct alignas(32) SinCosRow2 { double P, p, Q, q; };    // lock-step rows, see sincos_core
 struct PowLogRow { double invc, logc, logctail; };
+struct alignas(32) TanRow { double x, f, g, pad; };            // xfg of s_tan.c: x_i, tan x_i, cot x_i
 
 #if defined(__CUDACC__)
 static __device__ const LogRow g_log_tab[128] = GLIBC_LOG_TAB;
@@ -57,15 +58,18 @@ static __device__ __align__(32) const double g_sincos_tab[440] = GLIBC_SINCOS_TA
 static __device__ const SinCosRow2 g_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static __device__ __align__(16) const unsigned long long g_exp_tab[256] = GLIBC_EXP_TAB;
 static __device__ const PowLogRow g_pow_tab[128] = GLIBC_POW_TAB;
+static __device__ const TanRow g_tan_tab[186] = GLIBC_TAN_XFG;
 static __device__ const LogRow g_logf_tab[16] = GLIBC_LOGF_TAB;
 static __device__ __align__(16) const unsigned long long g_expf_tab[32] = GLIBC_EXPF_TAB;
 static __constant__ double c_sincosf_tab[28] = GLIBC_SINCOSF_TAB;
+static __constant__ float c_tanf_t[13] = GLIBC_TANF_T;
 static __device__ const LogRow g_powf_tab[16] = GLIBC_POWF_TAB;
 static __constant__ double c_powf_poly[5] = GLIBC_POWF_POLY;
 static __constant__ double c_exp2f_poly[3] = GLIBC_EXP2F_POLY;
 static __constant__ double c_logf_poly[3] = GLIBC_LOGF_POLY;
 static __constant__ double c_expf_poly[3] = GLIBC_EXPF_POLY;
 static __constant__ double c_pow_poly[7] = GLIBC_POW_POLY;
+static __constant__ double c_erfc_pool[58] = GLIBC_ERFC_POOL;
 static __constant__ double c_log_poly[5] = GLIBC_LOG_POLY;
 static __constant__ double c_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
@@ -75,15 +79,18 @@ static const double h_sincos_tab[440] = GLIBC_SINCOS_TAB;
 static const SinCosRow2 h_sincos_rows[220] = GLIBC_SINCOS_ROWS;
 static const unsigned long long h_exp_tab[256] = GLIBC_EXP_TAB;
 static const PowLogRow h_pow_tab[128] = GLIBC_POW_TAB;
+static const TanRow h_tan_tab[186] = GLIBC_TAN_XFG;
 static const LogRow h_logf_tab[16] = GLIBC_LOGF_TAB;
 static const unsigned long long h_expf_tab[32] = GLIBC_EXPF_TAB;
 static const double h_sincosf_tab[28] = GLIBC_SINCOSF_TAB;
+static const float h_tanf_t[13] = GLIBC_TANF_T;
 static const LogRow h_powf_tab[16] = GLIBC_POWF_TAB;
 static const double h_powf_poly[5] = GLIBC_POWF_POLY;
 static const double h_exp2f_poly[3] = GLIBC_EXP2F_POLY;
 static const double h_logf_poly[3] = GLIBC_LOGF_POLY;
 static const double h_expf_poly[3] = GLIBC_EXPF_POLY;
 static const double h_pow_poly[7] = GLIBC_POW_POLY;
+static const double h_erfc_pool[58] = GLIBC_ERFC_POOL;
 static const double h_log_poly[5] = GLIBC_LOG_POLY;
 static const double h_log_poly1[11] = GLIBC_LOG_POLY1;
 #endif
@@ -117,11 +124,16 @@ GM_FN void exp_row(int i, uint64_t& tail, uint64_t& sbits) {
   const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(&g_exp_tab[2 * i]));
   tail = v.x; sbits = v.y;
 }
-GM_FN double exp_out_of_range(double x) { return ::exp(x); }
 GM_FN PowLogRow pow_row(int i) {
   return PowLogRow{__ldg(&g_pow_tab[i].invc), __ldg(&g_pow_tab[i].logc), __ldg(&g_pow_tab[i].logctail)};
 }
 GM_FN double pow_special(double x, double y) { return ::pow(x, y); }
+GM_FN TanRow tan_row(int i) {
+  const double2* p = reinterpret_cast<const double2*>(&g_tan_tab[i]);
+  const double2 a = __ldg(p);
+  return TanRow{a.x, a.y, __ldg(&g_tan_tab[i].g), 0.0};
+}
+GM_FN double tan_huge(double x) { return ::tan(x); }
 // single precision: one IEEE float operation each, never contracted
 GM_FN float ff_add(float a, float b) { return __fadd_rn(a, b); }
 GM_FN float ff_sub(float a, float b) { return __fadd_rn(a, -b); }
@@ -139,6 +151,8 @@ GM_FN uint64_t expf_row(int i) { return __ldg(&g_expf_tab[i]); }
 GM_FN float logf_special(float x) { return ::logf(x); }
 GM_FN float expf_special(float x) { return ::expf(x); }
 GM_FN float cosf_large(float x) { return ::cosf(x); }
+GM_FN float tanf_large(float x) { return ::tanf(x); }
+GM_FN float ff_i2f(int k) { return __int2float_rn(k); }
 GM_FN LogRow powf_row(int i) {
   const double2 v = __ldg(reinterpret_cast<const double2*>(&g_powf_tab[i]));
   return LogRow{v.x, v.y};
@@ -147,9 +161,11 @@ GM_FN float powf_special(float x, float y) { return ::powf(x, y); }
 #define GM_POWF_POLY c_powf_poly
 #define GM_EXP2F_POLY c_exp2f_poly
 #define GM_SINCOSF c_sincosf_tab
+#define GM_TANF_T c_tanf_t
 #define GM_LOGF_POLY c_logf_poly
 #define GM_EXPF_POLY c_expf_poly
 #define GM_POW_POLY c_pow_poly
+#define GM_ERFC_POOL c_erfc_pool
 #define GM_LOG_POLY c_log_poly
 #define GM_LOG_POLY1 c_log_poly1
 #else
@@ -168,9 +184,10 @@ GM_FN SinCosRow sincos_row(int k) {
 GM_FN SinCosRow2 sincos_row2(int i) { return h_sincos_rows[i]; }
 GM_FN double f_sel(bool c, double a, double b) { return c ? a : b; }
 GM_FN void exp_row(int i, uint64_t& tail, uint64_t& sbits) { tail = h_exp_tab[2 * i]; sbits = h_exp_tab[2 * i + 1]; }
-GM_FN double exp_out_of_range(double x) { return __builtin_exp(x); }
 GM_FN PowLogRow pow_row(int i) { return h_pow_tab[i]; }
 GM_FN double pow_special(double x, double y) { return __builtin_pow(x, y); }
+GM_FN TanRow tan_row(int i) { return h_tan_tab[i]; }
+GM_FN double tan_huge(double x) { return __builtin_tan(x); }
 GM_FN float ff_add(float a, float b) { volatile float r = a + b; return r; }
 GM_FN float ff_sub(float a, float b) { volatile float r = a - b; return r; }
 GM_FN float ff_mul(float a, float b) { volatile float r = a * b; return r; }
@@ -184,14 +201,18 @@ GM_FN uint64_t expf_row(int i) { return h_expf_tab[i]; }
 GM_FN float logf_special(float x) { return __builtin_logf(x); }
 GM_FN float expf_special(float x) { return __builtin_expf(x); }
 GM_FN float cosf_large(float x) { return __builtin_cosf(x); }
+GM_FN float tanf_large(float x) { return __builtin_tanf(x); }
+GM_FN float ff_i2f(int k) { return static_cast<float>(k); }
 GM_FN LogRow powf_row(int i) { return h_powf_tab[i]; }
 GM_FN float powf_special(float x, float y) { return __builtin_powf(x, y); }
 #define GM_POWF_POLY h_powf_poly
 #define GM_EXP2F_POLY h_exp2f_poly
 #define GM_SINCOSF h_sincosf_tab
+#define GM_TANF_T h_tanf_t
 #define GM_LOGF_POLY h_logf_poly
 #define GM_EXPF_POLY h_expf_poly
 #define GM_POW_POLY h_pow_poly
+#define GM_ERFC_POOL h_erfc_pool
 #define GM_LOG_POLY h_log_poly
 #define GM_LOG_POLY1 h_log_poly1
 #endif
@@ -327,14 +348,38 @@ GM_FN void log_positive_normal_batch(const double (&x)[N], double (&lg)[N]) {
 // ============================================================================
 // sysdeps/ieee754/dbl-64/e_exp.c (Szabolcs Nagy): x = k ln2 / 128 + r, 2^(k/128) from
 // a 128-row table {tail, scale bits}, degree-5 polynomial in r; the FMA build's
-// fused operations written out.  2^-54 <= |x| < 512 here; smaller arguments give
-// 1 + x as in the library; larger ones (over / underflow handling, results that
-// are 0, inf or next to the subnormal range) go to the platform's exp.
+// fused operations written out, the scaled evaluation next to over- and underflow
+// (specialcase(): 512 <= |x| < 1024) included; non-finite arguments and |x| >= 1024
+// give IEEE's inf / 0 / NaN.
+// specialcase() of e_exp.c / e_pow.c (positive scale): 2^k may be out of range although
+// the result is not
+GM_FN double exp_specialcase(double tmp, uint64_t sbits, uint64_t ki) {
+  if ((ki & 0x80000000ull) == 0) {                       // k > 0: scale's exponent may have overflowed
+    const double sc = f_from_bits(sbits - (1009ull << 52));
+    return f_mul(f_fma(sc, tmp, sc), 0x1p1009);
+  }
+  const double sc = f_from_bits(sbits + (1022ull << 52));     // k < 0: care in the subnormal range
+  const double st = f_mul(tmp, sc);
+  double y = f_add(sc, st);
+  if (y < 1.0) {
+    const double hi = f_add(y, 1.0);
+    const double l0 = f_add(f_sub(sc, y), st);
+    y = f_sub(f_add(f_add(f_add(f_sub(1.0, hi), y), l0), hi), 1.0);
+    if (y == 0.0) y = 0.0;
+  }
+  return f_mul(y, 0x1p-1022);
+}
+
 GM_FN double exp(double x) {
-  const uint32_t abstop = static_cast<uint32_t>(f_bits(x) >> 52) & 0x7ffu;
+  uint32_t abstop = static_cast<uint32_t>(f_bits(x) >> 52) & 0x7ffu;
   if (abstop - 0x3c9u > 0x3eu) {
     if (abstop < 0x3c9u) return f_add(1.0, x);          // |x| < 2^-54
-    return exp_out_of_range(x);
+    if (abstop >= 0x409u) {                              // |x| >= 1024, inf, NaN
+      if (f_bits(x) == 0xfff0000000000000ull) return 0.0;
+      if (abstop >= 0x7ffu) return f_add(1.0, x);
+      return (f_bits(x) >> 63) ? 0.0 : f_from_bits(0x7ff0000000000000ull);
+    }
+    abstop = 0;                                          // 512 <= |x| < 1024
   }
   const double zs = f_fma(x, GLIBC_EXP_INVLN2N, GLIBC_EXP_SHIFT);
   const uint64_t ki = f_bits(zs);
@@ -350,6 +395,7 @@ GM_FN double exp(double x) {
   const double p45 = f_fma(r, GLIBC_EXP_C5, GLIBC_EXP_C4);
   const double lo = f_fma(p23, r2, tr);
   const double tmp = f_fma(f_mul(r2, r2), p45, lo);
+  if (abstop == 0) return exp_specialcase(tmp, sbits, ki);
   const double scale = f_from_bits(sbits);
   return f_fma(scale, tmp, scale);
 }
@@ -360,14 +406,43 @@ GM_FN double exp(double x) {
 // sysdeps/ieee754/dbl-64/e_pow.c (Szabolcs Nagy): log(x) as hi + lo with ~68 bits
 // from a 128-row table {1/c, log c, tail} and a degree-7 polynomial, y log(x) as
 // ehi + elo, then exp's table and polynomial with the tail folded in; the FMA
-// build's fused operations written out.  Main path only: x positive and normal,
-// 2^-65 <= |y| < 2^63, |y log x| in [2^-54, 512); everything else (zero /
-// negative / subnormal / non-finite x, huge or tiny y, over- and underflow) is
+// build's fused operations written out.  x positive and normal, 2^-65 <= |y| < 2^63
+// (results through over- and underflow included); everything else (zero /
+// negative / subnormal / non-finite x, huge or tiny y) is
 // the platform's pow -- the samplers raise uniforms to moderate powers.
+// checkint() of e_pow.c: 0 = y is not an integer, 1 = odd, 2 = even
+GM_FN int pow_checkint(uint64_t iy) {
+  const int e = static_cast<int>(iy >> 52) & 0x7ff;
+  if (e < 0x3ff) return 0;
+  if (e > 0x3ff + 52) return 2;
+  if (iy & ((1ull << (0x3ff + 52 - e)) - 1)) return 0;
+  if (iy & (1ull << (0x3ff + 52 - e))) return 1;
+  return 2;
+}
+
+GM_FN double pow_positive(uint64_t ix, double y);
+
 GM_FN double pow(double x, double y) {
   const uint64_t ix = f_bits(x), iy = f_bits(y);
   const uint32_t topx = static_cast<uint32_t>(ix >> 52), topy = static_cast<uint32_t>(iy >> 52);
-  if (topx - 1u > 0x7fdu || (topy & 0x7ffu) - 0x3beu > 0x7fu) return pow_special(x, y);
+  if ((topy & 0x7ffu) - 0x3beu > 0x7fu) return pow_special(x, y);
+  uint64_t ax = ix;
+  bool negate = false;
+  if (topx - 1u > 0x7fdu) {
+    // a negative normal base with an integer exponent: the library goes on with |x| and
+    // sets the sign of the scale factor for an odd exponent -- the negated result, bit for bit
+    if ((topx & 0x800u) == 0 || (topx & 0x7ffu) - 1u > 0x7fdu) return pow_special(x, y);
+    const int yint = pow_checkint(iy);
+    if (yint == 0) return pow_special(x, y);
+    ax = ix & 0x7fffffffffffffffull;
+    negate = yint == 1;
+  }
+  const double r = pow_positive(ax, y);
+  return negate ? f_neg(r) : r;
+}
+
+// x = from_bits(ix) positive and normal, 2^-65 <= |y| < 2^63
+GM_FN double pow_positive(uint64_t ix, double y) {
   const double* A = GM_POW_POLY;
   // log_inline
   const uint64_t tmp = ix - 0x3fe6955500000000ull;
@@ -403,8 +478,12 @@ GM_FN double pow(double x, double y) {
   double elo = f_fma(lhi, y, -ehi);
   elo = f_fma(y, llo, elo);
   // exp_inline
-  const uint32_t abstop = static_cast<uint32_t>(f_bits(ehi) >> 52) & 0x7ffu;
-  if (abstop - 0x3c9u > 0x3eu) return pow_special(x, y);
+  uint32_t abstop = static_cast<uint32_t>(f_bits(ehi) >> 52) & 0x7ffu;
+  if (abstop - 0x3c9u > 0x3eu) {
+    if (abstop < 0x3c9u) return f_add(1.0, ehi);         // |y log x| < 2^-54
+    if (abstop >= 0x409u) return (f_bits(ehi) >> 63) ? 0.0 : f_from_bits(0x7ff0000000000000ull);
+    abstop = 0;                                          // 512 <= |y log x| < 1024
+  }
   const double zs = f_fma(ehi, GLIBC_EXP_INVLN2N, GLIBC_EXP_SHIFT);
   const uint64_t ki = f_bits(zs);
   const double kd2 = f_sub(zs, GLIBC_EXP_SHIFT);
@@ -420,6 +499,7 @@ GM_FN double pow(double x, double y) {
   const double q45 = f_fma(rr, GLIBC_EXP_C5, GLIBC_EXP_C4);
   const double lo5 = f_fma(q23, r2, tr);
   const double tmp2 = f_fma(f_mul(r2, r2), q45, lo5);
+  if (abstop == 0) return exp_specialcase(tmp2, sbits, ki);
   const double scale = f_from_bits(sbits);
   return f_fma(tmp2, scale, scale);
 }
@@ -695,6 +775,253 @@ GM_FN double cos_medium(double x) {
   return ((n + 1) & 2) ? f_neg(r) : r;
 }
 
+// ---------------------------------------------------------------------------
+// tan (s_tan.c, the IBM routine with its multi-precision fall-backs removed, as
+// shipped since glibc 2.28; operation order and fusing follow __tan_fma).
+// The cauchy sampler and the Poisson Cauchy-envelope regime call tan(pi u), u in (0, 1].
+// ---------------------------------------------------------------------------
+
+// tan or -cot of the reduced argument a + da (|a| <= pi/4): cases VI / VII (and their
+// copies for the 25 < |x| <= 1e8 reduction) of __tan
+GM_FN double tan_reduced(double a, double da, int n) {
+  const bool neg = a < 0.0;
+  const double ya = neg ? f_neg(a) : a;
+  if (ya <= GLIBC_TAN_G2) {
+    const double a2 = f_mul(a, a);
+    double t2 = f_fma(a2, GLIBC_TAN_D11, GLIBC_TAN_D9);
+    t2 = f_fma(a2, t2, GLIBC_TAN_D7);
+    t2 = f_fma(a2, t2, GLIBC_TAN_D5);
+    t2 = f_fma(a2, t2, GLIBC_TAN_D3);
+    t2 = f_fma(f_mul(a, a2), t2, da);
+    const double b = f_add(a, t2);
+    if (n == 0) return b;
+    // -cot: EADD(a, t2, b, db); DIV2(1, 0, b, db, c, dc); -(c + dc)
+    const double db = (f_abs(a) > f_abs(t2)) ? f_add(f_sub(a, b), t2) : f_add(f_sub(t2, b), a);
+    const double c = f_div(1.0, b);
+    const double u = f_mul(c, b);
+    const double uu = f_fma(c, b, -u);
+    double r = f_sub(1.0, u);
+    r = f_sub(r, uu);
+    r = f_add(r, 0.0);
+    r = f_fma(-db, c, r);
+    const double cc = f_div(r, b);
+    const double z = f_add(c, cc);
+    const double zz = f_add(f_sub(c, z), cc);
+    return f_neg(f_add(zz, z));
+  }
+  const double yya = neg ? f_neg(da) : da;
+  const int i = static_cast<int>(f_fma(ya, 256.0, -15.5));
+  const TanRow row = tan_row(i);
+  const double z = f_add(f_sub(ya, row.x), yya);
+  const double z2 = f_mul(z, z);
+  const double pz = f_fma(f_mul(z, z2), f_fma(z2, GLIBC_TAN_E1, GLIBC_TAN_E0), z);
+  const double num = f_mul(f_add(row.f, row.g), pz);
+  if (n) {
+    const double y = f_sub(row.g, f_div(num, f_add(pz, row.f)));
+    return neg ? y : f_neg(y);                       // -sy * y
+  }
+  const double y = f_add(f_div(num, f_sub(row.g, pz)), row.f);
+  return neg ? f_neg(y) : y;                         // sy * y
+}
+
+GM_FN double tan(double x) {
+  const uint32_t hx = static_cast<uint32_t>(f_bits(x) >> 32);
+  if ((hx & 0x7ff00000u) == 0x7ff00000u) return f_sub(x, x);
+  const double w = f_abs(x);
+  if (w <= GLIBC_TAN_G1) return x;
+  if (w <= GLIBC_TAN_G2) {
+    const double x2 = f_mul(x, x);
+    double t2 = f_fma(x2, GLIBC_TAN_D11, GLIBC_TAN_D9);
+    t2 = f_fma(x2, t2, GLIBC_TAN_D7);
+    t2 = f_fma(x2, t2, GLIBC_TAN_D5);
+    t2 = f_fma(x2, t2, GLIBC_TAN_D3);
+    return f_fma(f_mul(x, x2), t2, x);
+  }
+  if (w <= GLIBC_TAN_G3) {
+    const int i = static_cast<int>(f_fma(w, 256.0, -15.5));
+    const TanRow row = tan_row(i);
+    const double z = f_sub(w, row.x);
+    const double z2 = f_mul(z, z);
+    const double pz = f_fma(f_mul(z, z2), f_fma(z2, GLIBC_TAN_E1, GLIBC_TAN_E0), z);
+    const double t2 = f_div(f_mul(f_add(row.f, row.g), pz), f_sub(row.g, pz));
+    const double y = f_add(t2, row.f);
+    return (x < 0.0) ? f_neg(y) : y;
+  }
+  if (w > GLIBC_TAN_G5) return tan_huge(x);
+  const double t = f_fma(x, GLIBC_SC_HPINV, GLIBC_SC_TOINT);
+  const double xn = f_sub(t, GLIBC_SC_TOINT);
+  const int n = static_cast<int>(static_cast<uint32_t>(f_bits(t))) & 1;
+  double t1 = f_fma(-xn, GLIBC_SC_MP1, x);
+  t1 = f_fma(-xn, GLIBC_SC_MP2, t1);
+  if (w <= GLIBC_TAN_G4) {
+    const double a = f_fma(-xn, GLIBC_TAN_MP3, t1);
+    const double da = f_fma(-xn, GLIBC_TAN_MP3, f_sub(t1, a));
+    return tan_reduced(a, da, n);
+  }
+  const double a0 = f_fma(-xn, GLIBC_SC_PP3, t1);
+  double da = f_fma(-xn, GLIBC_SC_PP3, f_sub(t1, a0));
+  const double a1 = f_fma(-xn, GLIBC_SC_PP4, a0);
+  da = f_add(da, f_fma(-xn, GLIBC_SC_PP4, f_sub(a0, a1)));
+  const double a = f_add(a1, da);
+  const double db = (f_abs(a1) > f_abs(da)) ? f_add(f_sub(a1, a), da) : f_add(f_sub(da, a), a1);
+  return tan_reduced(a, db, n);
+}
+
+// ---------------------------------------------------------------------------
+// log1p (s_log1p.c: fdlibm's routine with glibc's split polynomial; fusing as in
+// __log1p_fma).  Used by the cauchy log-density and the negative binomial's
+// large-size limit.  x > -1 and finite here; the rest: IEEE special values.
+// ---------------------------------------------------------------------------
+GM_FN double log1p(double x) {
+  const int32_t hx = static_cast<int32_t>(f_bits(x) >> 32);
+  const int32_t ax = hx & 0x7fffffff;
+  int k = 1;
+  int32_t hu = 1;
+  double f = x, c = 0.0;
+  if (hx < 0x3fda827a) {                                    // x < 0.41422
+    if (ax >= 0x3ff00000) {                                 // x <= -1
+      if (x == -1.0) return f_div(-0x1p54, 0.0);
+      const double d = f_sub(x, x);
+      return f_div(d, d);
+    }
+    if (ax < 0x3e200000) {                                  // |x| < 2^-29
+      if (ax < 0x3c900000) return x;
+      return f_fma(-f_mul(x, x), 0.5, x);
+    }
+    if (hx > 0 || hx <= static_cast<int32_t>(0xbfd2bec3u)) k = 0;     // -0.2929 < x < 0.41422
+  } else if (hx >= 0x7ff00000) {
+    return f_add(x, x);
+  }
+  if (k != 0) {
+    double u;
+    if (hx < 0x43400000) {
+      u = f_add(1.0, x);
+      hu = static_cast<int32_t>(f_bits(u) >> 32);
+      k = (hu >> 20) - 1023;
+      c = (k > 0) ? f_sub(1.0, f_sub(u, x)) : f_sub(x, f_sub(u, 1.0));
+      c = f_div(c, u);
+    } else {
+      u = x;
+      hu = hx;
+      k = (hu >> 20) - 1023;
+    }
+    hu &= 0x000fffff;
+    const uint64_t lo = f_bits(u) & 0xffffffffull;
+    if (hu < 0x6a09e) {
+      u = f_from_bits((static_cast<uint64_t>(static_cast<uint32_t>(hu) | 0x3ff00000u) << 32) | lo);
+    } else {
+      k += 1;
+      u = f_from_bits((static_cast<uint64_t>(static_cast<uint32_t>(hu) | 0x3fe00000u) << 32) | lo);
+      hu = (0x00100000 - hu) >> 2;
+    }
+    f = f_sub(u, 1.0);
+  }
+  const double hfsq = f_mul(f_mul(0.5, f), f);
+  const double kd = f_i2d(k);
+  if (hu == 0) {                                            // |f| < 2^-20
+    if (f == 0.0) {
+      if (k == 0) return 0.0;
+      return f_fma(kd, GLIBC_LOG1P_LN2_HI, f_fma(kd, GLIBC_LOG1P_LN2_LO, c));
+    }
+    const double R = f_mul(hfsq, f_fma(-f, GLIBC_LOG1P_TWO_THIRDS, 1.0));
+    if (k == 0) return f_sub(f, R);
+    return f_fma(kd, GLIBC_LOG1P_LN2_HI, -f_sub(f_sub(R, f_fma(kd, GLIBC_LOG1P_LN2_LO, c)), f));
+  }
+  const double s = f_div(f, f_add(2.0, f));
+  const double z = f_mul(s, s);
+  const double R2 = f_fma(z, GLIBC_LOG1P_LP3, GLIBC_LOG1P_LP2);
+  const double R3 = f_fma(z, GLIBC_LOG1P_LP5, GLIBC_LOG1P_LP4);
+  const double R4 = f_fma(z, GLIBC_LOG1P_LP7, GLIBC_LOG1P_LP6);
+  const double z2 = f_mul(z, z);
+  const double z4 = f_mul(z2, z2);
+  const double z6 = f_mul(z4, z2);
+  double R = f_fma(z, GLIBC_LOG1P_LP1, f_mul(z2, R2));
+  R = f_fma(z4, R3, R);
+  R = f_fma(z6, R4, R);
+  const double t = f_mul(f_add(R, hfsq), s);
+  if (k == 0) return f_sub(f, f_sub(hfsq, t));
+  const double e = f_add(f_fma(kd, GLIBC_LOG1P_LN2_LO, c), t);
+  return f_fma(kd, GLIBC_LOG1P_LN2_HI, -f_sub(f_sub(hfsq, e), f));
+}
+
+// ---------------------------------------------------------------------------
+// erfc (s_erf.c: fdlibm's routine with glibc's split polynomials; plain SSE2 code in the
+// library -- not an ifunc, nothing fused).  C[] is the routine's constant pool in the
+// library's own order: a coefficient the code subtracts is stored as its magnitude, so the
+// additions and subtractions below are the library's.  The two exponentials are e_exp.c
+// (exp above).  Used by the truncated normal density.
+// ---------------------------------------------------------------------------
+GM_FN double erfc(double x) {
+  const double* C = GM_ERFC_POOL;
+  const int32_t hx = static_cast<int32_t>(f_bits(x) >> 32);
+  const int32_t ix = hx & 0x7fffffff;
+  if (ix >= 0x7ff00000) return f_add(f_i2d(static_cast<int>((static_cast<uint32_t>(hx) >> 31) << 1)), f_div(1.0, x));
+  if (ix < 0x3feb0000) {                                    // |x| < 0.84375
+    if (ix < 0x3c700000) return f_sub(1.0, x);
+    const double z = f_mul(x, x);
+    const double z2 = f_mul(z, z);
+    const double z4 = f_mul(z2, z2);
+    const double r2 = f_sub(f_mul(C[0], z), C[1]);
+    const double r1 = f_add(f_mul(C[2], z), C[3]);
+    const double s2 = f_add(f_mul(C[5], z), C[6]);
+    const double s1 = f_add(f_mul(C[7], z), 1.0);
+    const double s3 = f_add(f_mul(z, C[8]), C[9]);
+    const double r = f_add(f_mul(C[4], z4), f_add(f_mul(r2, z2), r1));
+    const double sd = f_add(f_mul(s3, z4), f_add(f_mul(s2, z2), s1));
+    const double xy = f_mul(f_div(r, sd), x);
+    if (hx < 0x3fd00000) return f_sub(1.0, f_add(xy, x));
+    return f_sub(0.5, f_add(f_sub(x, 0.5), xy));
+  }
+  if (ix < 0x3ff40000) {                                    // 0.84375 <= |x| < 1.25
+    const double s = f_sub(f_abs(x), 1.0);
+    const double s2 = f_mul(s, s);
+    const double s4 = f_mul(s2, s2);
+    const double s6 = f_mul(s2, s4);
+    double P = f_add(f_mul(f_sub(f_mul(C[10], s), C[11]), s2), f_sub(f_mul(C[12], s), C[13]));
+    P = f_add(P, f_mul(f_sub(f_mul(C[14], s), C[15]), s4));
+    P = f_add(P, f_mul(C[16], s6));
+    double Q = f_add(f_mul(f_add(f_mul(C[17], s), C[18]), s2), f_add(f_mul(C[19], s), 1.0));
+    Q = f_add(f_mul(f_add(f_mul(s, C[20]), C[21]), s4), Q);
+    Q = f_add(Q, f_mul(s6, C[22]));
+    const double pq = f_div(P, Q);
+    if (hx < 0) return f_add(1.0, f_add(pq, C[23]));
+    return f_sub(C[57], pq);
+  }
+  if (ix < 0x403c0000) {                                    // |x| < 28
+    const double ax = f_abs(x);
+    const double s = f_div(1.0, f_mul(x, x));
+    const double s2 = f_mul(s, s);
+    const double s4 = f_mul(s2, s2);
+    const double s6 = f_mul(s2, s4);
+    double R, S;
+    if (ix < 0x4006db6d) {                                  // |x| < 1 / 0.35
+      R = f_add(f_mul(f_sub(f_mul(C[26], s), C[27]), s2), f_sub(f_mul(C[28], s), C[29]));
+      R = f_add(R, f_mul(f_sub(f_mul(C[30], s), C[31]), s4));
+      R = f_add(R, f_mul(f_sub(f_mul(C[32], s), C[33]), s6));
+      S = f_add(f_mul(f_add(f_mul(C[34], s), C[35]), s2), f_add(1.0, f_mul(C[36], s)));
+      S = f_add(S, f_mul(f_add(f_mul(C[37], s), C[38]), s4));
+      S = f_add(f_mul(f_add(f_mul(s, C[39]), C[40]), s6), S);
+      S = f_add(S, f_mul(f_mul(s4, s4), C[41]));
+    } else {
+      if (hx < 0 && ix >= 0x40180000) return f_sub(2.0, C[25]);         // x < -6
+      R = f_add(f_mul(f_sub(f_mul(C[42], s), C[43]), s2), f_sub(f_mul(C[44], s), C[45]));
+      R = f_add(R, f_mul(f_sub(f_mul(C[46], s), C[47]), s4));
+      R = f_add(R, f_mul(C[48], s6));
+      S = f_add(f_mul(f_add(f_mul(C[49], s), C[50]), s2), f_add(1.0, f_mul(C[51], s)));
+      S = f_add(S, f_mul(f_add(f_mul(C[52], s), C[53]), s4));
+      S = f_add(S, f_mul(f_add(f_mul(s, C[54]), C[55]), s6));
+    }
+    const double z = f_from_bits(f_bits(ax) & 0xffffffff00000000ull);
+    const double e1 = glibc::exp(f_sub(f_mul(f_neg(z), z), C[56]));
+    const double e2 = glibc::exp(f_add(f_mul(f_sub(z, ax), f_add(z, ax)), f_div(R, S)));
+    const double r = f_mul(e2, e1);
+    if (hx > 0) return f_div(r, ax);
+    return f_sub(2.0, f_div(r, ax));
+  }
+  if (hx > 0) return f_mul(C[25], C[25]);
+  return f_sub(2.0, C[25]);
+}
+
 // ============================================================================
 // single precision (real_type = float): logf, expf, cosf, lgammaf
 // ============================================================================
@@ -776,6 +1103,79 @@ GM_FN float cosf(float x) {
   const double* p = (n & 2) ? T + 14 : T;
   const double x2 = f_mul(xr, xr);
   return sincosf_poly((n & 1) ? f_mul(xr, sgn) : xr, x2, p, n ^ 1);
+}
+
+// k_tanf.c (fdlibm's kernel in float arithmetic, no contraction): tan(x + y) for iy = 1,
+// -1 / tan(x + y) for iy = -1, |x| <= pi / 4
+GM_FN float kernel_tanf(float x, float y, int iy) {
+  const float* T = GM_TANF_T;
+  const uint32_t hx = ff_bits(x);
+  const uint32_t ix = hx & 0x7fffffffu;
+  if (ix < 0x39000000u) {                                    // |x| < 2^-13, (int) x == 0
+    if ((ix | static_cast<uint32_t>(iy + 1)) == 0) return ff_div(1.0f, ff_from_bits(ix));
+    if (iy == 1) return x;
+    return ff_div(-1.0f, x);
+  }
+  const bool big = ix >= 0x3f2ca140u;                        // |x| >= 0.6744
+  if (big) {
+    if (hx >> 31) { x = ff_from_bits(hx ^ 0x80000000u); y = ff_from_bits(ff_bits(y) ^ 0x80000000u); }
+    const float z = ff_sub(GLIBC_TANF_PIO4, x);
+    const float w = ff_sub(GLIBC_TANF_PIO4LO, y);
+    x = ff_add(z, w);
+    y = 0.0f;
+    if (ff_from_bits(ff_bits(x) & 0x7fffffffu) < 0x1p-13f) {
+      const int sg = (1 - static_cast<int>((hx >> 30) & 2u)) * iy;
+      return ff_mul(ff_i2f(sg), ff_sub(1.0f, ff_mul(ff_i2f(2 * iy), x)));
+    }
+  }
+  const float z = ff_mul(x, x);
+  const float w = ff_mul(z, z);
+  float r = ff_add(ff_mul(T[11], w), T[9]);
+  r = ff_add(ff_mul(r, w), T[7]);
+  r = ff_add(ff_mul(r, w), T[5]);
+  r = ff_add(ff_mul(r, w), T[3]);
+  r = ff_add(ff_mul(r, w), T[1]);
+  float v = ff_add(ff_mul(T[12], w), T[10]);
+  v = ff_add(ff_mul(v, w), T[8]);
+  v = ff_add(ff_mul(v, w), T[6]);
+  v = ff_add(ff_mul(v, w), T[4]);
+  v = ff_add(ff_mul(v, w), T[2]);
+  v = ff_mul(z, v);
+  const float s = ff_mul(z, x);
+  r = ff_add(y, ff_mul(z, ff_add(ff_mul(s, ff_add(r, v)), y)));
+  r = ff_add(r, ff_mul(T[0], s));
+  const float wx = ff_add(x, r);
+  if (big) {
+    const float vi = ff_i2f(iy);
+    const float q = ff_sub(ff_div(ff_mul(wx, wx), ff_add(wx, vi)), r);
+    const float e = ff_sub(x, q);
+    const float res = ff_sub(vi, ff_add(e, e));
+    return ff_mul(ff_i2f(1 - static_cast<int>((hx >> 30) & 2u)), res);
+  }
+  if (iy == 1) return wx;
+  // -1 / (x + r) with the quotient's error corrected
+  const float zz = ff_from_bits(ff_bits(wx) & 0xfffff000u);
+  const float vv = ff_sub(r, ff_sub(zz, x));
+  const float a = ff_div(-1.0f, wx);
+  const float t = ff_from_bits(ff_bits(a) & 0xfffff000u);
+  const float ss = ff_add(1.0f, ff_mul(t, zz));
+  return ff_add(t, ff_mul(a, ff_add(ss, ff_mul(t, vv))));
+}
+
+// s_tanf.c (2.39): |x| <= pi / 4 straight to the kernel; below 120 the sincosf reduction
+// in double (x - n pi/2, unfused in this routine), split into a float head and tail.
+// Beyond 120 and for non-finite arguments: the platform's tanf.
+GM_FN float tanf(float x) {
+  const uint32_t ix = ff_bits(x) & 0x7fffffffu;
+  if (ix <= 0x3f490fdau) return kernel_tanf(x, 0.0f, 1);
+  if (((ix >> 20) & 0x7ffu) > 0x42eu) return tanf_large(x);
+  const double* P = GM_SINCOSF;
+  const double xd = f_f2d(x);
+  const int n = (static_cast<int>(f_mul(xd, P[4])) + 0x800000) >> 24;
+  const double xr = f_sub(xd, f_mul(f_i2d(n), P[5]));
+  const float y0 = f_d2f(xr);
+  const float y1 = f_d2f(f_sub(xr, f_f2d(y0)));
+  return kernel_tanf(y0, y1, 1 - ((n & 1) << 1));
 }
 
 // e_powf.c: log2(x) in double from a 16-row table and a degree-5 polynomial, y log2(x),

@@ -37,7 +37,7 @@ def inline_multinomial(state, size, prob):
     return out
 
 
-MATH_FN = {"log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4, "contraction_is_off": 5, "lgamma": 6, "exp": 7, "pow": 8}
+MATH_FN = {"log": 0, "log_normal": 1, "cos_0_2pi": 2, "sqrt_normal": 3, "sqrt": 4, "contraction_is_off": 5, "lgamma": 6, "exp": 7, "pow": 8, "tan": 9, "log1p": 10, "erfc": 11, "tanf": 12}
 
 
 def math_probe(fn, x):

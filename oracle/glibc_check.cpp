@@ -27,8 +27,12 @@ static inline uint64_t bits(double x) { uint64_t u; std::memcpy(&u, &x, 8); retu
 //      3: cos of 2 pi u, u in (0, 1]  (the Box-Muller angle)
 //      4: cos of values in [-8, 8]
 //      5: log of random bit patterns (special cases: negative, NaN, inf, subnormal)
+//      26-29: erfc on [-6, 6], [-30, 30], any bit pattern, magnitudes 2^-60 .. 32
+//      22-25: log1p on (-1, 2), any bit pattern, any positive normal, magnitudes 2^-60 .. 8
+//      18-21: tan of pi u, of [-30, 30], of every magnitude below 1.3e8, next to multiples of pi/2
+//      33, 34: pow(negative and positive bases, integer exponents), squares and cubes of any bit pattern
 //      15-17: pow(uniform, (0.05, 12)), pow(any positive normal, (-20, 20)), pow((0, 50), any bit pattern)
-//      13, 14: exp on [-700, 700] and on every magnitude below 2
+//      13, 14: exp on [-700, 700] and on every magnitude below 2; 30-32: [-1100, 1100], any bit pattern, subnormal results
 //      9-12: lgamma of positive arguments: (0, 10), any positive normal, (0.5, 300.5), integers and halves
 //      6, 7, 8: the lock-step formulation of cos on the Box-Muller angle, on
 //         [-1000, 1000], on log-uniform magnitudes below 1.0e8
@@ -72,6 +76,30 @@ extern "C" int64_t gm_compare(int kind, uint64_t seed, int64_t n, double* bad) {
                  { const double yy = 40 * (static_cast<double>(splitmix(s) >> 11) * 0x1p-53) - 20;
                    got = mb200::glibc::pow(x, yy); want = std::pow(x, yy); } break;
         case 17: x = 50 * u; { const double yy = from_bits(splitmix(s));                                        // any exponent
+                  got = mb200::glibc::pow(x, yy); want = std::pow(x, yy); } break;
+        case 18: x = M_PI * u; got = mb200::glibc::tan(x); want = std::tan(x); break;                            // the cauchy sampler's argument
+        case 19: x = 60 * u - 30; got = mb200::glibc::tan(x); want = std::tan(x); break;                         // both reductions below / above 25
+        case 20: x = from_bits(w & 0xc19fffffffffffffull);                                                       // any magnitude below 1.3e8, both signs
+                 got = mb200::glibc::tan(x); want = std::tan(x); break;
+        case 21: x = (static_cast<double>(1 + (w >> 40) % 64) + 0x1p-20 * (u - 0.5)) * M_PI_2;                   // next to the poles and zeros
+                 got = mb200::glibc::tan(x); want = std::tan(x); break;
+        case 22: x = 3 * u - 1; got = mb200::glibc::log1p(x); want = std::log1p(x); break;                       // (-1, 2): every branch on k
+        case 23: x = from_bits(w); got = mb200::glibc::log1p(x); want = std::log1p(x); break;                    // any bit pattern
+        case 24: x = from_bits((w >> 1) % 0x7fe0000000000000ull + 0x0010000000000000ull);                        // any positive normal
+                 got = mb200::glibc::log1p(x); want = std::log1p(x); break;
+        case 25: x = from_bits((w & 0x800fffffffffffffull) | (static_cast<uint64_t>(0x3ff - 60 + (w >> 52) % 64) << 52));  // small magnitudes, both signs
+                 got = mb200::glibc::log1p(x); want = std::log1p(x); break;
+        case 26: x = 12 * u - 6; got = mb200::glibc::erfc(x); want = std::erfc(x); break;                        // every polynomial piece
+        case 27: x = 60 * u - 30; got = mb200::glibc::erfc(x); want = std::erfc(x); break;                       // out to the underflow
+        case 28: x = from_bits(w); got = mb200::glibc::erfc(x); want = std::erfc(x); break;                      // any bit pattern
+        case 29: x = from_bits((w & 0x800fffffffffffffull) | (static_cast<uint64_t>(0x3ff - 60 + (w >> 52) % 65) << 52));  // magnitudes 2^-60 .. 32
+                 got = mb200::glibc::erfc(x); want = std::erfc(x); break;
+        case 30: x = 2200 * u - 1100; got = mb200::glibc::exp(x); want = std::exp(x); break;                     // through over- and underflow
+        case 31: x = from_bits(w); got = mb200::glibc::exp(x); want = std::exp(x); break;                        // any bit pattern
+        case 32: x = -(708 + 40 * u); got = mb200::glibc::exp(x); want = std::exp(x); break;                     // the subnormal results
+        case 33: x = 200 * u - 100; { const double yy = static_cast<double>(static_cast<int>(splitmix(s) % 41) - 20);   // negative bases, integer exponents
+                  got = mb200::glibc::pow(x, yy); want = std::pow(x, yy); } break;
+        case 34: x = from_bits(w); { const double yy = (splitmix(s) & 1) ? 2.0 : 3.0;                           // squares and cubes of anything
                   got = mb200::glibc::pow(x, yy); want = std::pow(x, yy); } break;
         default: x = from_bits(w); got = mb200::glibc::log(x); want = std::log(x); break;
       }
@@ -127,7 +155,7 @@ extern "C" int64_t gm_compare_lgamma_batch(uint64_t seed, int64_t n) {
   return mism;
 }
 // The float routines, EXHAUSTIVELY: every float bit pattern in [lo_bits, hi_bits) through
-// fn 0 = logf, 1 = expf, 2 = cosf, 3 = lgammaf (positive finite arguments only) against the
+// fn 0 = logf, 1 = expf, 2 = cosf, 4 = tanf, 3 = lgammaf (positive finite arguments only) against the
 // live libm; returns the number of differing results, *bad = the first offender's bits.
 extern "C" int64_t gm_compare_float(int fn, uint32_t lo_bits, uint32_t hi_bits, uint32_t* bad) {
   int64_t mism = 0;
@@ -142,6 +170,7 @@ extern "C" int64_t gm_compare_float(int fn, uint32_t lo_bits, uint32_t hi_bits, 
       case 0: got = mb200::glibc::logf(x); want = ::logf(x); break;
       case 1: got = mb200::glibc::expf(x); want = ::expf(x); break;
       case 2: got = mb200::glibc::cosf(x); want = ::cosf(x); break;
+      case 4: got = mb200::glibc::tanf(x); want = ::tanf(x); break;
       default: got = mb200::glibc::lgammaf_positive(x); want = ::lgammaf_r(x, &sg); break;
     }
     uint32_t gb, wb;
@@ -189,7 +218,7 @@ extern "C" double gm_log(double x) { return mb200::glibc::log(x); }
 extern "C" double gm_cos(double x) { return mb200::glibc::cos_medium(x); }
 extern "C" double gm_cos_lockstep(double x) { return mb200::glibc::cos_medium_lockstep(x); }
 
-// fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt, 4 = lgamma, 5 = pow(x[i], x[i ^ 1]) of the live libm, elementwise
+// fn 0 = log, 1 = cos, 2 = exp, 3 = sqrt, 4 = lgamma, 5 = pow(x[i], x[i ^ 1]), 6 = tan, 7 = log1p, 8 = erfc, 9 = tanf of the live libm, elementwise
 extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
@@ -199,6 +228,10 @@ extern "C" void gm_libm(int fn, const double* x, double* y, int64_t n) {
       case 2: y[i] = std::exp(x[i]); break;
       case 4: { int sg; y[i] = lgamma_r(x[i], &sg); break; }
       case 5: y[i] = std::pow(x[i], x[i ^ 1]); break;       // exponent: the neighbouring element (n even)
+      case 6: y[i] = std::tan(x[i]); break;
+      case 7: y[i] = std::log1p(x[i]); break;
+      case 8: y[i] = std::erfc(x[i]); break;
+      case 9: y[i] = static_cast<double>(::tanf(static_cast<float>(x[i]))); break;
       default: y[i] = std::sqrt(x[i]); break;
     }
   }

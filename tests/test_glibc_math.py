@@ -31,6 +31,23 @@ KINDS = {
     15: "pow(uniform, (0.05, 12)): the gamma / Weibull samplers' calls",
     16: "pow(any positive normal, (-20, 20))",
     17: "pow((0, 50), any bit pattern)",
+    33: "pow((-100, 100), integers in [-20, 20])",
+    34: "squares and cubes of any bit pattern",
+    18: "tan(pi u): the cauchy sampler's argument",
+    19: "tan on [-30, 30]: both reductions",
+    20: "tan of every magnitude below 1.3e8",
+    21: "tan next to multiples of pi / 2",
+    22: "log1p on (-1, 2)",
+    23: "log1p of any bit pattern",
+    24: "log1p of any positive normal double",
+    25: "log1p of magnitudes 2^-60 .. 8, both signs",
+    26: "erfc on [-6, 6]: every polynomial piece",
+    27: "erfc on [-30, 30]: out to the underflow",
+    28: "erfc of any bit pattern",
+    29: "erfc of magnitudes 2^-60 .. 32, both signs",
+    30: "exp on [-1100, 1100]: through over- and underflow",
+    31: "exp of any bit pattern",
+    32: "exp with subnormal results",
     6: "cos (lock-step formulation) of the Box-Muller angle",
     7: "cos (lock-step formulation) on [-1000, 1000]",
     8: "cos (lock-step formulation), magnitudes to 1e8",
@@ -72,14 +89,15 @@ def test_same_bits_as_libm(gm, kind):
 
 
 # every 16th float bit pattern by default (the whole set takes ~40 s on 8 cores:
-# MONTY_B200_GLIBC_FLOAT_STRIDE=1); the committed result of the exhaustive run is 0 / 0 / 0 / 0
+# MONTY_B200_GLIBC_FLOAT_STRIDE=1); the committed result of the exhaustive run is 0 differences for each
 FLOAT_STRIDE = int(os.environ.get("MONTY_B200_GLIBC_FLOAT_STRIDE", "16"))
 
 
 @pytest.mark.parametrize("fn,name,lo,hi", [(0, "logf", 0, 0xFFFFFFFF), (1, "expf", 0, 0xFFFFFFFF),
-                                          (2, "cosf", 0, 0xFF800000), (3, "lgammaf", 1, 0x7F800000)])
+                                          (2, "cosf", 0, 0xFF800000), (3, "lgammaf", 1, 0x7F800000),
+                                          (4, "tanf", 0, 0xFF800000)])
 def test_float_routines_same_bits_as_libm(gm, fn, name, lo, hi):
-    """real_type = float: logf / expf / cosf / lgammaf over the float bit patterns
+    """real_type = float: logf / expf / cosf / lgammaf / tanf over the float bit patterns
     (blocks of 2^20 patterns, every FLOAT_STRIDE-th block)."""
     bad = ctypes.c_uint32(0)
     block = 1 << 20
@@ -144,6 +162,12 @@ def test_tables_have_their_mathematical_meaning():
         c = 1 / mp.mpf(invc)
         assert abs(mp.log(c) - logc) < mp.mpf(2) ** -42, k
         assert struct.unpack("<Q", struct.pack("<d", logc))[0] & 0x1FF == 0 or logc == 0.0 or abs(logc) < 2 ** -8
+    xfg = macro("GLIBC_TAN_XFG")
+    assert len(xfg) == 186 * 4
+    for k in range(186):
+        xi, fi, gi = xfg[4 * k:4 * k + 3]
+        assert abs(xi - (k + 16) / 256) < 2 ** -24, k
+        assert abs(mp.tan(mp.mpf(xi)) - fi) < mp.mpf(2) ** -52 * fi and abs(mp.cot(mp.mpf(xi)) - gi) < mp.mpf(2) ** -52 * gi, k
     sc = macro("GLIBC_SINCOS_TAB")
     assert len(sc) == 440
     for k in range(110):

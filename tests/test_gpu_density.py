@@ -20,25 +20,13 @@ def gpu_density(mb, name, x, pars, log, rt="f64", **kw):
     return mb.density._density(name, x, pars, log, rt, **kw)
 
 
-# log-densities assembled from log, exp, lgamma (glibc's bits on the device,
-# include/monty_b200/detail/glibc_math.cuh) and IEEE arithmetic only: bit-identical
-BIT_EXACT_LOG = {"beta", "beta_binomial_ab", "beta_binomial_prob", "binomial", "exponential_mean", "exponential_rate",
-                 "gamma_rate", "gamma_scale", "hypergeometric", "log_normal", "negative_binomial_mu",
-                 "negative_binomial_prob", "normal", "poisson", "uniform", "zi_poisson",
-                 "zi_negative_binomial_mu", "zi_negative_binomial_prob"}
-
-
 @pytest.mark.parametrize("name", sorted(density_cases(4)))
 @pytest.mark.parametrize("log", [True, False])
 def test_double_parity(mb, oracle, name, log):
-    """The north-star's bar: log-densities within 4 ulp of the reference.
-    18 of the 21 are BIT-IDENTICAL in log form (BIT_EXACT_LOG) and within 1 ulp
-    in non-log form (identical unless the log-density is below -512, where exp
-    is the toolkit's).  The other three call log1p / pow / erf on the way
-    (cauchy, weibull, truncated_normal): the toolkit's routines, <= 2 ulp each,
-    checked to 4 ulp -- or, where the value is
-    a difference of much larger terms that cancel (cauchy's -log(pi) - log(scale)
-    - log1p(q^2) near zero, weibull's pow), to 8 eps of the largest term."""
+    """The north-star's bar is log-densities within 4 ulp of the reference.  All 21
+    are BIT-IDENTICAL, in log and in non-log form: each is assembled from log, exp,
+    pow, lgamma, log1p, erfc (glibc's bits on the device,
+    include/monty_b200/detail/glibc_math.cuh) and IEEE arithmetic only."""
     x, pars = density_cases(20000)[name]
     got = gpu_density(mb, name, x, pars, log)
     exp = oracle.density(name, x, pars, log)
@@ -46,34 +34,14 @@ def test_double_parity(mb, oracle, name, log):
     assert np.array_equal(np.isinf(got), np.isinf(exp))
     fin = np.isfinite(exp)
     d = ulp_distance(got[fin], exp[fin])
-    if name in BIT_EXACT_LOG:
-        assert d.max() <= (0 if log else 1), (name, log, d.max())
-        return
-    xs = np.abs(np.asarray(x, dtype=np.float64))[fin]
-    big = np.maximum.reduce([np.abs(np.asarray(p, dtype=np.float64))[fin] for p in pars] + [xs]) + 1.0
-    scale = big * np.log(big + 1.0) + 1.0           # size of the terms the value is assembled from
-    if not log:
-        with np.errstate(all="ignore"):
-            lg_ref = np.abs(oracle.density(name, x, pars, True)[fin])
-            scale = np.maximum(scale, np.where(np.isfinite(lg_ref), lg_ref, 0.0))
-    eps = np.finfo(np.float64).eps
-    # error in units of eps * (size of the terms the value is assembled from);
-    # for log = False the relative error of exp(v) is the absolute error of v
-    denom = eps * np.maximum(scale, np.abs(exp[fin])) if log else eps * scale * np.abs(exp[fin]) + 1e-300
-    units = np.abs(got[fin] - exp[fin]) / denom
-    ok = (d <= 4) | (units <= 8)
-    assert ok.all(), (name, d.max(), units.max())
-    assert np.median(np.minimum(d, units)) <= 1
+    assert d.max() == 0, (name, log, d.max())
 
 
 def test_fixture_parity(mb, golden):
     for name, (x, pars) in density_cases(129).items():
         got = gpu_density(mb, name, x, pars, True)
         exp = golden["density/f64/%s/1" % name]
-        if name in BIT_EXACT_LOG:
-            assert np.array_equal(got, exp, equal_nan=True), name
-        else:
-            assert np.allclose(got, exp, rtol=1e-12, atol=1e-12, equal_nan=True), name
+        assert np.array_equal(got, exp, equal_nan=True), name
 
 
 def test_float_variant(mb, oracle):

@@ -42,7 +42,7 @@ def libm():
     def call(fn, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)
-        lib.gm_libm({"log": 0, "cos": 1, "exp": 2, "sqrt": 3, "lgamma": 4, "pow": 5}[fn], x.ctypes.data, y.ctypes.data, x.size)
+        lib.gm_libm({"log": 0, "cos": 1, "exp": 2, "sqrt": 3, "lgamma": 4, "pow": 5, "tan": 6, "log1p": 7, "erfc": 8, "tanf": 9}[fn], x.ctypes.data, y.ctypes.data, x.size)
         return y
     return call
 
@@ -154,21 +154,18 @@ def test_lgamma_is_glibc_bit_for_bit(probe, libm):
 
 
 def test_exp_is_glibc_bit_for_bit(probe, libm):
-    """m_exp (glibc's e_exp.c restated) on [-512, 512) and tiny arguments: the same
-    bits as the host's libm; 512 <= |x| takes the toolkit's exp (results 0, inf
-    or next to the subnormal range) and has to agree to 1 ulp."""
+    """m_exp (glibc's e_exp.c restated, the scaled evaluation next to over- and
+    underflow included): the same bits as the host's libm for every argument."""
     rs = np.random.default_rng(7)
     n = max(1, N // 10)
     x = np.concatenate([rs.uniform(-512, 512, n), rs.uniform(-40, 3, n), rs.uniform(-1, 1, n) * 2.0 ** -rs.integers(0, 70, n).astype(np.float64),
                         np.array([0.0, -0.0, 1.0, -1.0, 2.0 ** -54, 2.0 ** -55, -2.0 ** -60, 511.999, -511.999, 709.0, -708.0])])
-    inner = (np.abs(x) < 512)
+    far = np.array([512.0, 600.0, 709.7, 709.79, -600.0, -708.3, -740.0, -745.2, -750.0, 720.0, 1024.0, -1024.0, 1e300, -1e300,
+                    np.inf, -np.inf, np.nan])
+    x = np.concatenate([x, far, rs.uniform(-1030, 1030, n), -rs.uniform(700, 750, n)])
     got, want = probe("exp", x), libm("exp", x)
-    ok = same_bits(got[inner], want[inner])
-    assert ok.all(), "first offender x = %s" % x[inner][~ok][0].hex()
-    far = np.array([512.0, 600.0, 709.7, -600.0, -708.3, -740.0, -750.0, 720.0])
-    g, w = probe("exp", far), libm("exp", far)
-    with np.errstate(invalid="ignore"):
-        assert ((g == w) | (np.abs(g - w) <= np.abs(np.spacing(w)))).all()
+    ok = same_bits(got, want)
+    assert ok.all(), "first offender x = %s" % x[~ok][0].hex()
 
 
 def test_pow_is_glibc_bit_for_bit(probe, libm):
@@ -186,17 +183,63 @@ def test_pow_is_glibc_bit_for_bit(probe, libm):
     y[0::2] = np.exp(rs.uniform(-300, 300, n // 2))
     y[1::2] = rs.uniform(0.1, 2.2, n // 2)
     got, want = probe("pow", y), libm("pow", y)
-    # |y log x| < 512, i.e. results between e^-512 and e^512, is the restated main path;
-    # beyond it the toolkit's pow answers (1 ulp)
-    with np.errstate(divide="ignore"):
-        main = np.isfinite(want) & (want != 0) & (np.abs(np.log(want)) < 511)
-    assert same_bits(got[main], want[main]).all()
-    rest = np.isfinite(want) & ~main
-    assert (np.abs(got[rest] - want[rest]) <= np.abs(np.spacing(want[rest]))).all()
+    # results through over- and underflow (specialcase() of e_pow.c) included
+    assert same_bits(got, want).all(), "first offender %s" % y[~same_bits(got, want)][:2]
+    # negative bases with integer exponents (the cauchy density squares (x - location) / scale
+    # through pow): the library's |x| path with the sign restored
+    z = np.empty(n)
+    z[0::2] = rs.uniform(-50, 50, n // 2)
+    z[1::2] = rs.integers(1, 4, n // 2).astype(np.float64)
+    got, want = probe("pow", z), libm("pow", z)
+    ok = same_bits(got, want) | (np.arange(n) % 2 == 1)          # odd slots: pow(integer, a real), not of interest
+    assert ok.all(), "first offender %s" % z[~ok][:2]
     odd = np.array([0.0, 2.5, 2.0, 0.0, -2.0, 3.0, 1.0, 1e300, np.inf, 0.5, 4.0, 0.5])
     g, w = probe("pow", odd), libm("pow", odd)
     with np.errstate(invalid="ignore"):
         assert (same_bits(g, w) | (np.abs(g - w) <= np.abs(np.spacing(w)))).all()
+
+
+def test_tan_is_glibc_bit_for_bit(probe, libm):
+    """m_tan (glibc's s_tan.c restated): tan(pi u) as the cauchy sampler and the Poisson
+    Cauchy-envelope regime call it, both reductions (|x| <= 25 and <= 1e8), next to the
+    poles; beyond 1e8 the toolkit's tan answers.  The float overload (s_tanf.c /
+    k_tanf.c) on the float cauchy argument and below 120."""
+    rs = np.random.default_rng(9)
+    n = max(1, N // 10)
+    k = rs.integers(1, 64, n).astype(np.float64)
+    x = np.concatenate([np.pi * random_reals(rs, n), rs.uniform(-30, 30, n), rs.uniform(-1, 1, n) * 10.0 ** rs.uniform(-9, 8, n),
+                        k * (np.pi / 2) * (1 + rs.uniform(-1e-7, 1e-7, n)), np.array([0.0, -0.0, 1e-9, 0.0608, 0.787, 25.0, 1e8, np.pi / 2, np.pi])])
+    got, want = probe("tan", x), libm("tan", x)
+    ok = same_bits(got, want)
+    assert ok.all(), "first offender x = %s" % x[~ok][0].hex()
+    far = np.array([1.5e8, 1e12, -3e15, 1e300])
+    g, w = probe("tan", far), libm("tan", far)
+    assert (np.abs(g - w) <= 2 * np.abs(np.spacing(w))).all()
+    xf = np.concatenate([(np.float32(np.pi) * random_reals(rs, n).astype(np.float32)).astype(np.float64),
+                         rs.uniform(-119, 119, n).astype(np.float32).astype(np.float64),
+                         (rs.uniform(-1, 1, n) * 2.0 ** -rs.integers(0, 30, n)).astype(np.float32).astype(np.float64)])
+    got, want = probe("tanf", xf), libm("tanf", xf)
+    ok = same_bits(got, want)
+    assert ok.all(), "first offender x = %s" % xf[~ok][0].hex()
+
+
+def test_log1p_and_erfc_are_glibc_bit_for_bit(probe, libm):
+    """m_log1p (s_log1p.c) and m_erfc (s_erf.c): the cauchy and truncated-normal densities'
+    last two libm calls; erfc's two exponentials are e_exp.c (m_exp)."""
+    rs = np.random.default_rng(10)
+    n = max(1, N // 10)
+    x = np.concatenate([rs.uniform(-1, 2, n), np.exp(rs.uniform(-60, 60, n)), -np.exp(rs.uniform(-60, 0, n)) * 0.999,
+                        np.array([0.0, -0.0, 2.0 ** -30, -2.0 ** -30, 2.0 ** -55, 0.41421, -0.2929, 1e300])])
+    got, want = probe("log1p", x), libm("log1p", x)
+    ok = same_bits(got, want)
+    assert ok.all(), "first offender x = %s" % x[~ok][0].hex()
+    x = np.concatenate([rs.uniform(-6.5, 28.5, n), rs.uniform(-1.3, 1.3, n), rs.uniform(-1, 1, n) * 2.0 ** -rs.integers(0, 60, n).astype(np.float64),
+                        np.array([0.0, -0.0, 0.84375, 1.25, 1 / 0.35, -6.0, 6.0, 22.0])])
+    got, want = probe("erfc", x), libm("erfc", x)
+    ok = same_bits(got, want)
+    assert ok.all(), "first offender x = %s" % x[~ok][0].hex()
+    far = np.array([22.7, 25.0, 26.5, 27.9, 28.0, 40.0, -7.0, -30.0, np.inf, -np.inf, np.nan])
+    assert same_bits(probe("erfc", far), libm("erfc", far)).all()
 
 
 def test_sqrt_is_correctly_rounded(probe):

@@ -6,19 +6,17 @@ Bars (BASELINE.json north_star):
   * uniform reals, final generator states: bit-exact;
   * integer-valued draws (double): bit-exact up to a mismatch fraction <= 1e-6
     attributable to libm ulp differences -- we assert 0 mismatches here;
-  * continuous draws (double): within 4 ulp.  The device's log and cos return
-    glibc's bits (include/monty_b200/detail/glibc_math.cuh), so every sampler assembled from log,
-    exp, pow, cos, sqrt and IEEE arithmetic alone -- exponential, the three
-    normals, truncated normal, log_normal, gamma, beta, weibull -- is asserted
-    BIT-IDENTICAL, shifted and scaled parameters included; cauchy (tan: the
-    toolkit's routine, <= 2 ulp) is held to 4 eps of the terms `location + scale *
-    tan` adds;
+  * continuous draws (double): within 4 ulp.  The device's log, exp, pow, cos and
+    tan return glibc's bits (include/monty_b200/detail/glibc_math.cuh), so all 12 continuous
+    samplers -- exponential, the three normals, truncated normal, log_normal,
+    gamma, beta, weibull, cauchy -- are asserted BIT-IDENTICAL, shifted and
+    scaled parameters included;
   * float real_type: bit-identical too (the north-star asks for 1e-6 relative):
     glibc's logf / expf / powf / cosf / lgammaf are restated bit for bit, which
     also makes the integer-valued float draws that subtract large lgammaf terms
     (Poisson lambda >~ 1e3, hypergeometric H2PE, negative binomial) exact --
     they depend on the last bit of the platform's float libm in the REFERENCE
-    ITSELF; cauchy (tanf) is the one sampler held to 1e-6 relative.
+    ITSELF; tanf (s_tanf.c / k_tanf.c) makes the float cauchy draws exact too.
 """
 import numpy as np
 import pytest
@@ -32,7 +30,7 @@ ALL = sorted(sampler_cases(4))
 CONTINUOUS = [n for n in ALL if n not in INTEGER_VALUED and n not in ("real", "uniform")]
 # log, exp, pow, cos, sqrt and IEEE arithmetic only: the same bits as the reference
 BIT_EXACT = {"exponential_rate", "exponential_mean", "normal_box_muller", "normal_polar", "normal_ziggurat",
-             "truncated_normal", "log_normal", "gamma_scale", "gamma_rate", "beta", "weibull"}
+             "truncated_normal", "log_normal", "gamma_scale", "gamma_rate", "beta", "weibull", "cauchy"}
 EPS = np.finfo(np.float64).eps
 
 
@@ -41,17 +39,6 @@ def assert_continuous_parity(name, y, exp, pars, n):
     if name in BIT_EXACT:
         bad = y != exp
         assert not bad.any(), (name, int(bad.sum()), y[bad][:3], exp[bad][:3])
-        return
-    if name in ("gamma_scale", "gamma_rate", "beta"):
-        # Marsaglia-Tsang on a bit-identical normal: identical unless a shape is
-        # below 1, where the draw is multiplied by pow(u, 1 / shape)
-        small = np.broadcast_to(np.atleast_1d(pars[0]), (n,)) < 1
-        if name == "beta":
-            small = small | (np.broadcast_to(np.atleast_1d(pars[1]), (n,)) < 1)
-        assert np.array_equal(y[~small], exp[~small]), name
-    if name == "cauchy":
-        loc = np.abs(np.broadcast_to(np.atleast_1d(pars[0]), (n,)))[:, None]
-        assert (np.abs(y - exp) <= 4 * EPS * (np.abs(exp) + loc)).all(), name
         return
     d = ulp_distance(y, exp)
     assert d.max() <= 4, (name, d.max())
@@ -158,20 +145,15 @@ def test_float_real_type_is_bit_identical(mb, oracle, name):
     checked against the host libm, exhaustively, in tests/test_glibc_math.py), so
     every sampler is bit-identical -- draws AND final states, the integer-valued
     ones whose accept tests subtract large lgammaf terms included (round 1: 0.5-3%
-    of those draws differed).  Only cauchy (tanf: the toolkit's) is held to 1e-6
-    relative instead."""
+    of those draws differed)."""
     n, ns = 8192, 32
     pars = sampler_cases(n)[name]
     y, st, _ = gpu_sample(mb, name, n, ns, pars, rt="f32")
     ost = oracle.seed_states(7, n)
     exp = oracle.sample(name, ost, ns, pars, "f32")
     assert np.array_equal(st, ost), "%d streams ended in a different state" % int((st != ost).any(axis=1).sum())
-    if name == "cauchy":
-        loc = np.abs(np.broadcast_to(np.atleast_1d(pars[0]), (n,)))[:, None]
-        assert (np.abs(y - exp) <= 1e-6 * (np.abs(exp) + loc)).all()
-    else:
-        same = (y == exp) | (np.isnan(y) & np.isnan(exp))
-        assert same.all(), (name, float(1 - same.mean()), y[~same][:3], exp[~same][:3])
+    same = (y == exp) | (np.isnan(y) & np.isnan(exp))
+    assert same.all(), (name, float(1 - same.mean()), y[~same][:3], exp[~same][:3])
 
 
 def test_empty_requests(mb):

@@ -249,6 +249,59 @@ def main(out=None):
     LGF["s0"] = -LGF["a0"]
     assert abs(LGF["tc"] - 1.46163214) < 1e-6 and abs(LGF["w0"] - 0.41893853) < 1e-6 and abs(LGF["w1"] - 1 / 12) < 1e-6
     assert LGF["w6"] < 0 and LGF["t13"] < 0 and abs(LGF["r1"] - 1.3920053) < 1e-6 and abs(LGF["u1"] - 0.63282706) < 1e-6
+    # ---- s_tan.c (IBM Accurate Mathematical Library, slow paths removed in 2.28+): the
+    # 186-row table xfg {x_i, tan x_i, cot x_i, (unused)} anchored on its published first row,
+    # and the scalars of utan.h, each confirmed present in .rodata
+    tn = find_doubles(blob, off, size, [float.fromhex("0x1.000001e519d60p-4"), float.fromhex("0x1.0055796c4e240p-4")])
+    if tn < 0:
+        raise SystemExit("tan table (xfg) signature not found")
+    xfg = dbl(blob, tn, 186 * 4)
+    for k in range(186):
+        xi, fi, gi = xfg[4 * k:4 * k + 3]
+        assert abs(xi - (k + 16) / 256) < 2 ** -25 and abs(fi - math.tan(xi)) < 1e-15 and abs(gi * fi - 1) < 1e-15, k
+    TAN = {
+        "g1": "0x1.b096cp-27", "g2": "0x1.f212dp-5", "g3": "0x1.92f1ap-1", "g4": "0x1.9p+4", "g5": "0x1.7d784p+26",
+        "d3": "0x1.5555555555555p-2", "d5": "0x1.11111111107c6p-3", "d7": "0x1.ba1ba1cdb8745p-5",
+        "d9": "0x1.664ed49cfc666p-6", "d11": "0x1.2385a3cf2e4eap-7",
+        "e0": "0x1.5555555554dbdp-2", "e1": "0x1.11112e0a6b45fp-3", "mp3": "-0x1.cb3b399d747f2p-55",
+    }
+    for name, hx in TAN.items():
+        if find_doubles(blob, off, size, [float.fromhex(hx)]) < 0:
+            missing.append("tan_" + name)
+    # ---- k_tanf.c (fdlibm, float arithmetic): pio4, pio4lo, 2^-13 and T[0..12] in the pool's order
+    # T12 T10 T8 T6 T4 T2 T11 T9 T7 T5 T3 T1 T0, anchored on {pio4, pio4lo}
+    tf_ = blob.find(struct.pack("<2I", 0x3f490fda, 0x33222168), off, off + size)
+    if tf_ < 0:
+        raise SystemExit("k_tanf constant pool not found")
+    tw = struct.unpack_from("<16f", blob, tf_)
+    order = (12, 10, 8, 6, 4, 2, 11, 9, 7, 5, 3, 1, 0)
+    TANF_T = [0.0] * 13
+    for pos, idx in enumerate(order):
+        TANF_T[idx] = tw[3 + pos]
+    assert tw[2] == 2.0 ** -13 and abs(TANF_T[0] - 1 / 3) < 1e-7 and abs(TANF_T[1] - 2 / 15) < 1e-7 and abs(TANF_T[2] - 17 / 315) < 1e-7
+    TANF_PIO4, TANF_PIO4LO = tw[0], tw[1]
+    # ---- s_log1p.c (fdlibm; FMA ifunc variant): published constants, confirmed present
+    LOG1P = {
+        "ln2_hi": "0x1.62e42fee00000p-1", "ln2_lo": "0x1.a39ef35793c76p-33", "two_thirds": "0x1.5555555555555p-1",
+        "lp1": "0x1.5555555555593p-1", "lp2": "0x1.999999997fa04p-2", "lp3": "0x1.2492494229359p-2",
+        "lp4": "0x1.c71c51d8e78afp-3", "lp5": "0x1.7466496cb03dep-3", "lp6": "0x1.39a09d078c69fp-3",
+        "lp7": "0x1.2f112df3e5244p-3",
+    }
+    for name, hx in LOG1P.items():
+        if find_doubles(blob, off, size, [float.fromhex(hx)]) < 0:
+            missing.append("log1p_" + name)
+    # ---- s_erf.c, erfc half (fdlibm with glibc's split polynomials; not an ifunc, no FMA).
+    # The compiler pooled the 58 constants of __erfc in order of first use and stored
+    # the magnitude of each coefficient the code subtracts; glibc_math.cuh's erfc indexes
+    # the pool the way the routine does.  Anchored on erx (index 23) and 1 - erx (57).
+    erx = float.fromhex("0x1.b0ac160000000p-1")
+    ex = find_doubles(blob, off, size, [erx])
+    while ex >= 0 and dbl(blob, ex + 8 * 34, 1)[0] != 1.0 - erx:
+        ex = find_doubles(blob, ex + 8, off + size - ex - 8, [erx])
+    if ex < 0:
+        raise SystemExit("erfc constant pool not found")
+    ERFC = dbl(blob, ex - 8 * 23, 58)
+    assert ERFC[56] == 0.5625 and ERFC[25] == 1e-300 and abs(ERFC[3] - 0.1283791670955126) < 1e-15, ERFC
     if out is None:
         return dict(ln2hi=ln2hi, lgamma=LG, ln2lo=ln2lo, A=A, B=B, T=T, sincos=sct, missing=missing,
                     log_addr=addr + (log_off - off), sincos_addr=addr + (j - off))
@@ -317,6 +370,25 @@ def main(out=None):
     L.append("#define GLIBC_EXP2F_POLY { %s }" % ", ".join(fh(v) for v in POWF["exp2_poly"]))
     L.append("/* __sincosf_table[2]: {sign[4], hpi_inv, hpi, c0, c1, s1, c2, s2, c3, s3, c4} */")
     L.append("#define GLIBC_SINCOSF_TAB { %s }" % ", ".join(fh(v) for v in SINCOSF))
+    L.append("/* s_tan.c: utan.h scalars and xfg[186] = {x_i, tan x_i, cot x_i}, x_i ~ (i + 16) / 256 */")
+    for name, hx in TAN.items():
+        L.append("#define GLIBC_TAN_%s %s" % (name.upper(), fh(float.fromhex(hx))))
+    L.append("#define GLIBC_TAN_XFG { \\")
+    for k in range(186):
+        L.append("  {%s, %s, %s, 0.0}, \\" % tuple(fh(v) for v in xfg[4 * k:4 * k + 3]))
+    L[-1] = L[-1][:-3] + " }"
+    L.append("/* k_tanf.c (fdlibm, float): T[13], pio4, pio4lo */")
+    L.append("#define GLIBC_TANF_T { %s }" % ", ".join(fhf(v) for v in TANF_T))
+    L.append("#define GLIBC_TANF_PIO4 %s" % fhf(TANF_PIO4))
+    L.append("#define GLIBC_TANF_PIO4LO %s" % fhf(TANF_PIO4LO))
+    L.append("/* s_log1p.c (fdlibm) */")
+    for name, hx in LOG1P.items():
+        L.append("#define GLIBC_LOG1P_%s %s" % (name.upper(), fh(float.fromhex(hx))))
+    L.append("/* s_erf.c: __erfc's constant pool in the library's order (see the tool) */")
+    L.append("#define GLIBC_ERFC_POOL { \\")
+    for k in range(0, 58, 4):
+        L.append("  " + ", ".join(fh(v) for v in ERFC[k:k + 4]) + ", \\")
+    L[-1] = L[-1][:-3] + " }"
     L.append("/* e_lgammaf_r.c (fdlibm, float) constants, signs as published */")
     for name in sorted(LGF, key=lambda n: (n.rstrip("0123456789_m"), int("".join(c for c in n if c.isdigit()) or 0))):
         L.append("#define GLIBC_LGF_%s %s" % (name.upper(), fhf(LGF[name])))
