@@ -20,6 +20,19 @@ int mb200_example_inline_draw(mb200_rng* rng, int dist, int real_type,
                               const double* const* params_host, const size_t* param_len,
                               double* out_host);
 
+/* The device-side API on the reference's other generators (generator_draw.cu): n_streams
+ * streams seeded like prng<G>(n_streams, seed) by monty_b200::device_prng<G>, then `jumps`
+ * jump()s and `long_jumps` long_jump()s of every stream, then n_samples draws of `dist` per
+ * stream through monty::random::<dist><real_type>(state, ...).  gen (MB200_GEN_*):
+ * XOSHIRO128PLUS (f32: generator<float>; f64 too), XOSHIRO256PLUS (generator<double>; f32
+ * too), XOSHIRO128STARSTAR (f32), XOSHIRO256STARSTAR / XOROSHIRO128PLUSPLUS /
+ * XOSHIRO512STARSTAR (f64).  out_host: n_streams x n_samples doubles, stream-major;
+ * state_out (optional): the final states, int_type[n_streams][state words] as exported. */
+int mb200_example_generator_draw(int gen, int dist, int real_type, uint64_t seed, size_t n_streams,
+                                 size_t n_samples, int jumps, int long_jumps,
+                                 const double* const* params_host, const size_t* param_len,
+                                 double* out_host, void* state_out);
+
 /* Bootstrap particle filter of the stochastic SIR model of the reference's
  * test-suite (tests/testthat/helper-sir-filter.R:56-117): n_particles =
  * n_streams of `system`, one stream in `filter` for the systematic

@@ -81,7 +81,11 @@ __device__ __forceinline__ uint64_t x256_next(X256& s) {
 
 // The sampler generator is xoshiro256+ (the reference's default_rng64,
 // src/random.cpp:10).
+// The samplers (samplers.cuh) are templates on the generator: anything with
+// `state_type s` and `int_type next()` (generators.cuh has the other eleven).
 struct Rng {
+  using state_type = X256;
+  using int_type = uint64_t;
   X256 s;
   __device__ __forceinline__ uint64_t next() { return x256_next<kPlus>(s); }
 };
@@ -102,13 +106,30 @@ __device__ __forceinline__ float u64_to_float(uint64_t x) {
   return __fmaf_rn(static_cast<float>(t), 2.3283064e-10f, (2.3283064e-10f / 2.0f));
 }
 
-template <typename T> __device__ __forceinline__ T int_to_real(uint64_t x);
-template <> __device__ __forceinline__ double int_to_real<double>(uint64_t x) { return u64_to_double(x); }
-template <> __device__ __forceinline__ float int_to_real<float>(uint64_t x) { return u64_to_float(x); }
+// hdr/utils.hpp:27-31, 40-44: a 32-bit generator's word.  x * 2^-32 is exact in double and
+// so is adding 2^-33; in float the conversion rounds once, the scaling is exact and the
+// addition rounds once, which one FMA reproduces.
+__device__ __forceinline__ double u32_to_double(uint32_t x) {
+  return __fma_rn(static_cast<double>(x), 2.3283064365386963e-10, (2.3283064365386963e-10 / 2.0));
+}
+__device__ __forceinline__ float u32_to_float(uint32_t x) {
+  return __fmaf_rn(static_cast<float>(x), 2.3283064e-10f, (2.3283064e-10f / 2.0f));
+}
+
+template <typename T> struct IntToReal;
+template <> struct IntToReal<double> {
+  __device__ __forceinline__ static double from(uint64_t x) { return u64_to_double(x); }
+  __device__ __forceinline__ static double from(uint32_t x) { return u32_to_double(x); }
+};
+template <> struct IntToReal<float> {
+  __device__ __forceinline__ static float from(uint64_t x) { return u64_to_float(x); }
+  __device__ __forceinline__ static float from(uint32_t x) { return u32_to_float(x); }
+};
+template <typename T, typename U> __device__ __forceinline__ T int_to_real(U x) { return IntToReal<T>::from(x); }
 
 // hdr/generator.hpp:154-159
-template <typename T>
-__device__ __forceinline__ T random_real(Rng& r) {
+template <typename T, typename R>
+__device__ __forceinline__ T random_real(R& r) {
   return int_to_real<T>(r.next());
 }
 

@@ -30,14 +30,16 @@
 //     `#ifndef __CUDA_ARCH__`);
 //   * invalid parameters: the reference prints and __trap()s, which kills the
 //     CUDA context; here the draw returns NaN (define MONTY_B200_TRAP_ON_ERROR
-//     for the reference's behaviour);
-//   * `generator<float>` is xoshiro256+ as well -- the generator the
-//     reference's R layer uses for every real_type (src/random.cpp:10) -- not
-//     xoshiro128+.
+//     for the reference's behaviour).
+// `generator<float>` is xoshiro128+ and `generator<double>` xoshiro256+, as in the
+// reference (hdr/random.hpp:31-47); every sampler works on any of the twelve state
+// types.  (The bulk C-ABI behind the R layer is xoshiro256+ for every real_type, like
+// src/random.cpp:10.)
 #pragma once
 #include <cstdio>
 
 #include "detail/samplers.cuh"
+#include "detail/generators.cuh"
 #include "detail/density.cuh"
 #include "detail/jump_constants.cuh"
 
@@ -90,16 +92,42 @@ __device__ __forceinline__ bool contraction_is_off() {
 }
 
 // ---- generator state -------------------------------------------------------
-// hdr/xoshiro_state.hpp:20-39 + hdr/xoshiro256.hpp: four 64-bit words.
-struct xoshiro256plus {
-  using int_type = uint64_t;
-  mb200::X256 s;
-  __host__ __device__ static constexpr size_t size() { return 4; }
-  __host__ __device__ uint64_t& operator[](size_t i) { return (&s.s0)[i]; }
-  __host__ __device__ const uint64_t& operator[](size_t i) const { return (&s.s0)[i]; }
+// hdr/xoshiro_state.hpp:20-39: the words of one stream, `state[i]` in the reference's
+// exported order (hdr/prng.hpp:92-105).  All twelve generators of the reference
+// (hdr/xoshiro128.hpp, xoroshiro128.hpp, xoshiro256.hpp, xoshiro512.hpp).
+template <class State, int SCR> struct xoshiro_state {
+  using int_type = typename mb200::GenTraits<State>::int_type;
+  using state_type = State;
+  static constexpr int scrambler = SCR;
+  State s;
+  __host__ __device__ static constexpr size_t size() { return mb200::GenTraits<State>::N; }
+  __host__ __device__ int_type& operator[](size_t i) { return mb200::gen_words(s)[i]; }
+  __host__ __device__ const int_type& operator[](size_t i) const { return mb200::gen_words(const_cast<State&>(s))[i]; }
 };
+using xoshiro256plus = xoshiro_state<mb200::X256, mb200::kPlus>;
+using xoshiro256plusplus = xoshiro_state<mb200::X256, mb200::kPlusPlus>;
+using xoshiro256starstar = xoshiro_state<mb200::X256, mb200::kStarStar>;
+using xoshiro128plus = xoshiro_state<mb200::X128, mb200::kPlus>;
+using xoshiro128plusplus = xoshiro_state<mb200::X128, mb200::kPlusPlus>;
+using xoshiro128starstar = xoshiro_state<mb200::X128, mb200::kStarStar>;
+using xoroshiro128plus = xoshiro_state<mb200::XR128, mb200::kPlus>;
+using xoroshiro128plusplus = xoshiro_state<mb200::XR128, mb200::kPlusPlus>;
+using xoroshiro128starstar = xoshiro_state<mb200::XR128, mb200::kStarStar>;
+using xoshiro512plus = xoshiro_state<mb200::X512, mb200::kPlus>;
+using xoshiro512plusplus = xoshiro_state<mb200::X512, mb200::kPlusPlus>;
+using xoshiro512starstar = xoshiro_state<mb200::X512, mb200::kStarStar>;
 
-template <typename real_type> using generator = xoshiro256plus;
+// hdr/random.hpp:31-47: xoshiro128+ for float, xoshiro256+ otherwise
+template <typename real_type> struct default_rng_helper { using type = xoshiro256plus; };
+template <> struct default_rng_helper<float> { using type = xoshiro128plus; };
+template <typename real_type> using generator = typename default_rng_helper<real_type>::type;
+
+namespace detail {
+// the samplers' view of a state type: xoshiro256+ takes the batch kernels' generator
+// (written on 32-bit halves), the others the plain restatements of generators.cuh
+template <class G> struct rng_of { using type = mb200::GenRng<typename G::state_type, G::scrambler>; };
+template <> struct rng_of<xoshiro256plus> { using type = mb200::Rng; };
+}  // namespace detail
 
 // state <-> the device array of monty_b200::prng (uint64[n_streams][4]),
 // 2 x 128-bit accesses per stream
@@ -108,6 +136,18 @@ __device__ __forceinline__ xoshiro256plus load_state(const uint64_t* states, siz
 }
 __device__ __forceinline__ void store_state(uint64_t* states, size_t stream, const xoshiro256plus& g) {
   mb200::store_state(states, stream, g.s);
+}
+// any generator: int_type[n_streams][size()], the layout of monty_b200::device_prng<G>
+// (device_prng.cuh) and of the reference's export_state()
+template <class G>
+__device__ __forceinline__ G load_state_of(const typename G::int_type* states, size_t stream) {
+  G g;
+  for (size_t i = 0; i < G::size(); ++i) g[i] = states[stream * G::size() + i];
+  return g;
+}
+template <class G>
+__device__ __forceinline__ void store_state_of(typename G::int_type* states, size_t stream, const G& g) {
+  for (size_t i = 0; i < G::size(); ++i) states[stream * G::size() + i] = g[i];
 }
 
 // hdr/utils.hpp:72-77, hdr/generator.hpp:114-141
@@ -120,25 +160,34 @@ __host__ __device__ inline uint64_t splitmix64(uint64_t seed) {
 template <typename rng_state_type>
 __host__ __device__ inline rng_state_type seed(uint64_t seed) {
   rng_state_type g;
-  for (int i = 0; i < 4; ++i) {
+  for (size_t i = 0; i < rng_state_type::size(); ++i) {
     seed = splitmix64(seed);
-    g[i] = seed;
+    g[i] = static_cast<typename rng_state_type::int_type>(seed);
   }
   return g;
 }
 
 // hdr/generator.hpp:59-106
-__device__ inline void jump(xoshiro256plus& g) { mb200::x256_apply_poly(g.s, mb200::kJump256); }
-__device__ inline void long_jump(xoshiro256plus& g) { mb200::x256_apply_poly(g.s, mb200::kLongJump256); }
+template <class State, int SCR>
+__host__ __device__ inline void jump(xoshiro_state<State, SCR>& g) { mb200::gen_jump<State, SCR, false>(g.s); }
+template <class State, int SCR>
+__host__ __device__ inline void long_jump(xoshiro_state<State, SCR>& g) { mb200::gen_jump<State, SCR, true>(g.s); }
 
 // hdr/generator.hpp:154-183
 template <typename T, typename rng_state_type>
 __device__ __forceinline__ T random_int(rng_state_type& g) {
-  return static_cast<T>(mb200::x256_next<mb200::kPlus>(g.s));
+  static_assert(sizeof(T) <= sizeof(typename rng_state_type::int_type), "requested integer too wide");
+  typename detail::rng_of<rng_state_type>::type r{g.s};
+  const auto value = r.next();
+  g.s = r.s;
+  return static_cast<T>(value);
 }
 template <typename real_type, typename rng_state_type>
 __device__ __forceinline__ real_type random_real(rng_state_type& g) {
-  return mb200::int_to_real<real_type>(mb200::x256_next<mb200::kPlus>(g.s));
+  typename detail::rng_of<rng_state_type>::type r{g.s};
+  const real_type v = mb200::random_real<real_type>(r);
+  g.s = r.s;
+  return v;
 }
 
 namespace detail {
@@ -151,7 +200,7 @@ __device__ __forceinline__ real_type draw(rng_state_type& g, const real_type (&p
     fail(what);
     return nan_value<real_type>();
   }
-  mb200::Rng r{g.s};
+  typename rng_of<rng_state_type>::type r{g.s};
   const real_type v = D::draw(r, q, c);
   g.s = r.s;
   if (D::DYN_ERR && c.err) {
@@ -256,7 +305,7 @@ __device__ inline void multinomial(rng_state_type& g, real_type size, const T& p
 // default (which gamma and truncated_normal use implicitly)
 template <typename real_type, algorithm::normal A = algorithm::normal::box_muller, typename rng_state_type>
 __device__ __forceinline__ real_type random_normal(rng_state_type& g) {
-  mb200::Rng r{g.s};
+  typename detail::rng_of<rng_state_type>::type r{g.s};
   real_type z;
   if (A == algorithm::normal::box_muller) {
     z = mb200::std_normal_box_muller<real_type>(r);

@@ -6,7 +6,7 @@ import os
 
 import numpy as np
 
-from ._lib import DIST, check, lib as _main  # noqa: F401  (loads libmonty_b200.so first)
+from ._lib import DIST, GENERATORS, check, lib as _main  # noqa: F401  (loads libmonty_b200.so first)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmonty_b200_examples.so")
@@ -16,6 +16,7 @@ lib = C.CDLL(LIB_PATH)
 lib.mb200_example_inline_draw.restype = C.c_int
 lib.mb200_example_sir_filter.restype = C.c_int
 lib.mb200_example_math_probe.restype = C.c_int
+lib.mb200_example_generator_draw.restype = C.c_int
 
 lib.mb200_example_inline_multinomial.restype = C.c_int
 
@@ -90,3 +91,33 @@ def sir_filter(system, filt, pars, data_time, data_incidence, resample=True, ret
         C.c_int(1 if resample else 0), C.byref(ll),
         final.ctypes.data_as(C.c_void_p) if final is not None else None))
     return (ll.value, final) if return_state else ll.value
+
+
+# state words per stream and their width, by generator family
+GEN_LAYOUT = {"xoshiro256": (4, np.uint64), "xoshiro128": (4, np.uint32), "xoroshiro128": (2, np.uint64),
+              "xoshiro512": (8, np.uint64)}
+
+
+def generator_layout(gen):
+    for scr in ("plusplus", "starstar", "plus"):
+        if gen.endswith(scr):
+            return GEN_LAYOUT[gen[:-len(scr)]]
+    raise ValueError(gen)
+
+
+def generator_draw(gen, dist, seed, n_streams, n_samples, params=(), real_type="f64", jumps=0, long_jumps=0):
+    """The device-side API on another generator (examples/generator_draw.cu): streams seeded
+    like the reference's prng<gen>(n_streams, seed), then jumps, then n_samples draws of
+    `dist` per stream through monty::random::<dist><real_type>(state, ...).  Returns
+    (draws (n_streams, n_samples), final states (n_streams, words))."""
+    arrs = [np.ascontiguousarray(np.atleast_1d(np.asarray(p, dtype=np.float64))) for p in params]
+    ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs] + [None] * (4 - len(arrs)))
+    lens = (C.c_size_t * 4)(*[a.size for a in arrs] + [0] * (4 - len(arrs)))
+    words, wt = generator_layout(gen)
+    out = np.empty((n_streams, n_samples), dtype=np.float64)
+    st = np.empty((n_streams, words), dtype=wt)
+    check(lib.mb200_example_generator_draw(
+        C.c_int(GENERATORS.index(gen)), C.c_int(DIST[dist]), C.c_int(1 if real_type == "f32" else 0),
+        C.c_uint64(seed), C.c_size_t(n_streams), C.c_size_t(n_samples), C.c_int(jumps), C.c_int(long_jumps),
+        ptrs, lens, out.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
+    return out, st

@@ -53,8 +53,8 @@ struct input {  // ref: src/random.cpp:21-42
   double operator[](size_t i) const { return data[fixed ? 0 : i]; }
 };
 
-template <typename real_type>
-real_type draw_one(int dist, rng256p& s, const input* p, size_t i) {
+template <typename real_type, typename G = rng256p>
+real_type draw_one(int dist, G& s, const input* p, size_t i) {
   using T = real_type;
   const T a = p[0].data ? static_cast<T>(p[0][i]) : 0;
   const T b = p[1].data ? static_cast<T>(p[1][i]) : 0;
@@ -245,9 +245,59 @@ void density_impl(int dens, size_t n, const void* x, int x_is_i32,
 
 }  // namespace
 
+// prng<G>(n, seed) -> jumps -> n_samples draws per stream, for any generator
+// ref: hdr/prng.hpp:29-73, src/random.cpp:211-228
+template <typename real_type, typename G>
+int generator_draw_impl(int dist, uint64_t seed, size_t n_streams, size_t n_samples,
+                        int jumps, int long_jumps, const input* p, double* out, void* state_out) {
+  mr::prng<G> r(n_streams, mr::seed_data<G>(seed), false);
+  for (int k = 0; k < jumps; ++k) r.jump();
+  for (int k = 0; k < long_jumps; ++k) r.long_jump();
+  for (size_t i = 0; i < n_streams; ++i) {
+    for (size_t j = 0; j < n_samples; ++j) {
+      out[n_samples * i + j] = draw_one<real_type, G>(dist, r.state(i), p, i);
+    }
+  }
+  if (state_out) {
+    const auto v = r.export_state();
+    std::memcpy(state_out, v.data(), v.size() * sizeof(typename G::int_type));
+  }
+  return 0;
+}
+
 extern "C" {
 
 const char* ref_last_error(void) { return g_err.c_str(); }
+
+// the reference's samplers instantiated on its other generators (default for float:
+// xoshiro128+, hdr/random.hpp:31-47); mirrors examples/generator_draw.cu
+int ref_generator_draw(int gen, int dist, int real_type, uint64_t seed, size_t n_streams,
+                       size_t n_samples, int jumps, int long_jumps,
+                       const double* const* params, const size_t* param_len,
+                       double* out, void* state_out) {
+  input p[MB200_MAX_PARAMS] = {};
+  const int np = (dist >= 0 && dist < MB200_DIST_COUNT) ? k_n_params[dist] : -1;
+  if (np < 0) { g_err = "unknown distribution id"; return -2; }
+  for (int k = 0; k < np; ++k) p[k] = input{params[k], param_len[k] == 1};
+  const bool f32 = real_type == MB200_REAL_F32;
+  try {
+#define GD(T, G) return generator_draw_impl<T, G>(dist, seed, n_streams, n_samples, jumps, long_jumps, p, out, state_out)
+    switch (gen) {
+    case MB200_GEN_XOSHIRO128PLUS:
+      if (f32) GD(float, mr::generator<float>); else GD(double, mr::xoshiro128plus);
+    case MB200_GEN_XOSHIRO256PLUS:
+      if (f32) GD(float, mr::xoshiro256plus); else GD(double, mr::generator<double>);
+    case MB200_GEN_XOSHIRO256STARSTAR: if (!f32) GD(double, mr::xoshiro256starstar); break;
+    case MB200_GEN_XOROSHIRO128PLUSPLUS: if (!f32) GD(double, mr::xoroshiro128plusplus); break;
+    case MB200_GEN_XOSHIRO512STARSTAR: if (!f32) GD(double, mr::xoshiro512starstar); break;
+    case MB200_GEN_XOSHIRO128STARSTAR: if (f32) GD(float, mr::xoshiro128starstar); break;
+    default: break;
+    }
+#undef GD
+  } catch (const std::exception& e) { g_err = e.what(); return -3; }
+  g_err = "unsupported generator / real type";
+  return -2;
+}
 
 int ref_max_threads(void) {
 #ifdef _OPENMP

@@ -158,6 +158,32 @@ class Oracle:
             raise OracleError(self._err())
         return out
 
+    def generator_draw(self, gen, dist, seed, n_streams, n_samples, params=(), real_type="f64",
+                       jumps=0, long_jumps=0):
+        """The reference's samplers instantiated on another generator (reference
+        build only): prng<gen>(n_streams, seed), jumps, n_samples draws per stream.
+        Returns (draws, final states as exported)."""
+        d = DIST[dist]
+        arrs = [np.ascontiguousarray(np.atleast_1d(p), dtype=np.float64) for p in params]
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs] + [None] * (4 - len(arrs)))
+        lens = (C.c_size_t * 4)(*[a.size for a in arrs] + [0] * (4 - len(arrs)))
+        fam = gen
+        for scr in ("plusplus", "starstar", "plus"):
+            if gen.endswith(scr):
+                fam = gen[:-len(scr)]
+                break
+        words, wt = {"xoshiro256": (4, np.uint64), "xoshiro128": (4, np.uint32),
+                     "xoroshiro128": (2, np.uint64), "xoshiro512": (8, np.uint64)}[fam]
+        out = np.full((n_streams, n_samples), np.nan, dtype=np.float64)
+        st = np.zeros((n_streams, words), dtype=wt)
+        rc = self._fn("generator_draw")(C.c_int(GEN_NAMES.index(gen)), C.c_int(d), C.c_int(1 if real_type == "f32" else 0),
+                                        C.c_uint64(seed), C.c_size_t(n_streams), C.c_size_t(n_samples),
+                                        C.c_int(jumps), C.c_int(long_jumps), ptrs, lens,
+                                        out.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise OracleError(self._err())
+        return out, st
+
     def sir_filter(self, system_state, filter_state, pars, data_time, data_incidence, resample=True):
         """The SIR particle filter of the reference's test-suite over the
         reference's C++ samplers (oracle/ref_harness.cpp, reference kind only).
