@@ -179,6 +179,9 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   asm volatile("{\n\t"
                ".reg .pred p;\n\t"
@@ -196,12 +199,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 // doubles per thread are a 32-byte stride: two wavefronts per load).
 // (is_int is a compile-time fact after unrolling)
 template <typename T>
-__device__ __forceinline__ void lds_four(uint32_t array_saddr, int tid, bool is_int, T (&v)[4]) {
+__device__ __forceinline__ void lds_four(uint32_t array_saddr, int tid, bool is_int, T (&v)[4], int* raw = nullptr) {
   if (is_int) {
     int2 a, b;
     asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "r"(array_saddr + tid * 8));
     asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(b.x), "=r"(b.y) : "r"(array_saddr + (kDensTile / 2) * 4 + tid * 8));
     v[0] = static_cast<T>(a.x); v[1] = static_cast<T>(a.y); v[2] = static_cast<T>(b.x); v[3] = static_cast<T>(b.y);
+    if (raw) { raw[0] = a.x; raw[1] = a.y; raw[2] = b.x; raw[3] = b.y; }
   } else {
     const double2 a = lds_f64x2(array_saddr + tid * 16), b = lds_f64x2(array_saddr + (kDensTile / 2) * 8 + tid * 16);
     v[0] = static_cast<T>(a.x); v[1] = static_cast<T>(a.y); v[2] = static_cast<T>(b.x); v[3] = static_cast<T>(b.y);
@@ -213,14 +217,21 @@ __device__ __forceinline__ void lds_four(uint32_t array_saddr, int tid, bool is_
 // together and the four logs run as one batch (independent chains hide the table
 // latency; the window around 1 is worked off jointly) -- the same operations on
 // the same values as four calls of dens_poisson (hdr/density.hpp:173-189).
+// xi: the observations as the int32 they arrived as (Poisson's canonical layout), or null:
+// lgamma(x + 1) is then table[xi + 1] without the round trip through double
 template <int DENS, typename T, int NPD>
-__device__ __forceinline__ void density_compute4(const T (&x)[4], const T (&p)[NPD > 0 ? NPD : 1][4], bool lg, double (&v)[4]) {
+__device__ __forceinline__ void density_compute4(const T (&x)[4], const T (&p)[NPD > 0 ? NPD : 1][4], bool lg, double (&v)[4],
+                                                 const int* xi = nullptr, const double* __restrict__ lgt = nullptr) {
   if constexpr (DENS == MB200_DENS_POISSON && sizeof(T) == 8) {
     double lgm[4], ll[4];
     bool plain = true;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      lgm[u] = m_lgamma(x[u] + 1);
+      if (xi != nullptr && lgt != nullptr && static_cast<unsigned>(xi[u]) < static_cast<unsigned>(kLgtN - 1)) {
+        lgm[u] = __ldg(lgt + xi[u] + 1);            // the bits m_lgamma(x + 1) returns (same table)
+      } else {
+        lgm[u] = m_lgamma(x[u] + 1);
+      }
       const uint64_t ix = glibc::f_bits(p[0][u]);
       plain = plain && (ix - 0x0010000000000000ull < 0x7fe0000000000000ull);      // positive, finite, normal
     }
@@ -255,14 +266,17 @@ density_tile_kernel(const DensityArgs a, const unsigned long long n_full_tiles) 
   constexpr int NPD = DensNP<DENS>::value;
   constexpr int NA = Cn::n_arrays;
   extern __shared__ __align__(128) unsigned char dens_smem[];
-  __shared__ __align__(8) unsigned long long mbar_store[kDensStages];
+  __shared__ __align__(8) unsigned long long mbar_store[2 * kDensStages];   // full[s], then empty[s]
   const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(dens_smem));
   const uint32_t mbar0 = static_cast<uint32_t>(__cvta_generic_to_shared(mbar_store));
   const int tid = threadIdx.x;
   const bool lg = a.log != 0;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kDensStages; ++s) mbar_init(mbar0 + 8 * s, 1);
+    for (int s = 0; s < kDensStages; ++s) {
+      mbar_init(mbar0 + 8 * s, 1);
+      mbar_init(mbar0 + 8 * (kDensStages + s), kDensBlock / 32);      // one arrival per warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -293,18 +307,25 @@ density_tile_kernel(const DensityArgs a, const unsigned long long n_full_tiles) 
 
   double acc = 0.0;
   unsigned it = 0;
+  const double* __restrict__ lgt = g_lgt_d;           // lgamma of small integers (samplers.cuh), read once
   for (unsigned long long tile = blockIdx.x; tile < n_full_tiles; tile += step, ++it) {
     const int s = static_cast<int>(it % kDensStages);
     mbar_wait(mbar0 + 8 * s, (it / kDensStages) & 1u);
     const uint32_t base = smem0 + s * Cn::stage_bytes;
     T x[4], p[NPD > 0 ? NPD : 1][4];
-    lds_four<T>(base + Cn::offset(0), tid, Cn::is_int(0), x);
+    int xi[4];
+    lds_four<T>(base + Cn::offset(0), tid, Cn::is_int(0), x, xi);
 #pragma unroll
     for (int k = 0; k < NPD; ++k) lds_four<T>(base + Cn::offset(k + 1), tid, Cn::is_int(k + 1), p[k]);
-    __syncthreads();                        // every thread holds its observations: the stage is free
+    // This warp holds its observations: one arrival on the stage's "empty" barrier.  Only the
+    // issuing thread waits for all eight (a block-wide barrier here made every warp wait for
+    // the slowest one of each tile: ncu barrier stall 0.97 per issue, r02 summary).
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(mbar0 + 8 * (kDensStages + s));
+    if (tid == 0 && tile + kDensStages * step < n_full_tiles) mbar_wait(mbar0 + 8 * (kDensStages + s), (it / kDensStages) & 1u);
     issue(tile + kDensStages * step, s);
     double v[4];
-    density_compute4<DENS, T, NPD>(x, p, lg, v);
+    density_compute4<DENS, T, NPD>(x, p, lg, v, Cn::is_int(0) ? xi : nullptr, lgt);
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc += v[u];
     if (a.out) {
