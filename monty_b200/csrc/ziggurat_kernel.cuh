@@ -48,6 +48,20 @@
 #ifndef MB200_ZIG_BARE
 #define MB200_ZIG_BARE 0
 #endif
+// MEASUREMENT ONLY (never the shipped build): 1 = the full per-word instruction stream
+// (wedge machinery included), but every lane stores and advances its slot pointer on
+// every word, so lanes never drift apart: no drift-induced shared-memory store conflicts
+// and no clean-up iterations.  Bounds what a tile layout immune to drift could gain
+// (WRONG draws).
+#ifndef MB200_ZIG_NODRIFT
+#define MB200_ZIG_NODRIFT 0
+#endif
+// MEASUREMENT ONLY: 1 = pointers drift and clean-up iterations run as shipped, but the
+// tile store goes to a column that depends on the iteration only (conflict free whatever
+// the drift): isolates the cost of the drift-induced store conflicts (WRONG draws)
+#ifndef MB200_ZIG_NOCONF
+#define MB200_ZIG_NOCONF 0
+#endif
 
 namespace mb200 {
 
@@ -156,6 +170,9 @@ struct ZigLane {
   float wzs;         // z^2 * log2(e) / 2 of the parked candidate (single precision)
   uint32_t widx;     // parked layer * 128 + copy offset
   uint32_t p;        // shared address of the next output slot
+#if MB200_ZIG_NOCONF
+  uint32_t q, qbase;
+#endif
   T mean, sd;
 };
 
@@ -209,7 +226,14 @@ __device__ __forceinline__ void zig_word(ZigLane<T, OutT>& L, uint32_t zig_saddr
   const double zx = u0 * xy.x;
   const T zt = static_cast<T>(zx);
   const OutT fy = static_cast<OutT>(STANDARD ? zt : zt * L.sd + L.mean);
+#if MB200_ZIG_NODRIFT
+  sts_out(L.p, fy);
+#elif MB200_ZIG_NOCONF
+  if (!L.wedge) sts_out(L.qbase + L.q, fy);
+  L.q = (L.q + sizeof(OutT)) & (32 * sizeof(OutT) - 1);      // 32 columns round and round, the same for every lane
+#else
   if (!L.wedge) sts_out(L.p, fy);
+#endif
 
 #if MB200_ZIG_BARE
   if (fast) L.p = bump(L.p, sizeof(OutT));
@@ -242,8 +266,14 @@ __device__ __forceinline__ void zig_word(ZigLane<T, OutT>& L, uint32_t zig_saddr
   // address is below 2^23, so as a float bit pattern it is a subnormal, and
   // adding the subnormal whose pattern is sizeof(OutT) is exact integer addition
   // (no flush-to-zero in this translation unit)
+#if MB200_ZIG_NODRIFT
+  // two pointer updates per word as in the shipped build, net one slot whatever happened
+  L.p = bump(L.p, fast ? 2 * sizeof(OutT) : sizeof(OutT));
+  if (fast) L.p = L.p - sizeof(OutT);
+#else
   if (fast) L.p = bump(L.p, sizeof(OutT));
   if (wemit) L.p = bump(L.p, sizeof(OutT));
+#endif
   if (park) {
     const float4 w = lds_f32x4(wtab_lane_saddr + (idx >> 3));
     const float zr = __fmaf_rn(m, w.z, w.w);
@@ -352,6 +382,10 @@ __device__ __forceinline__ void ziggurat_body(const SampleArgs& a) {
       remaining -= cnt;
       const uint32_t extra = remaining < kLead ? remaining : kLead;     // never past the end of the stream's batch
       L.p = row_saddr + (e_lo + lead) * kSz;
+#if MB200_ZIG_NOCONF
+      L.q = 0;
+      L.qbase = row_saddr;
+#endif
       const uint32_t p_end = row_saddr + (e_lo + cnt) * kSz;
       const uint32_t p_cap = p_end + extra * kSz;
       const uint32_t n_hot = __reduce_min_sync(0xffffffffu, (p_cap - L.p) / kSz);
