@@ -39,8 +39,11 @@
 
 #if defined(__CUDACC__)
 #define GM_FN __host__ __device__ __forceinline__
+// cold paths (results next to over- / underflow): out of line, so the hot callers do not grow
+#define GM_COLD static __host__ __device__ __noinline__
 #else
 #define GM_FN static inline
+#define GM_COLD static
 #endif
 
 namespace mb200 {
@@ -353,7 +356,7 @@ GM_FN void log_positive_normal_batch(const double (&x)[N], double (&lg)[N]) {
 // give IEEE's inf / 0 / NaN.
 // specialcase() of e_exp.c / e_pow.c (positive scale): 2^k may be out of range although
 // the result is not
-GM_FN double exp_specialcase(double tmp, uint64_t sbits, uint64_t ki) {
+GM_COLD double exp_specialcase(double tmp, uint64_t sbits, uint64_t ki) {
   if ((ki & 0x80000000ull) == 0) {                       // k > 0: scale's exponent may have overflowed
     const double sc = f_from_bits(sbits - (1009ull << 52));
     return f_mul(f_fma(sc, tmp, sc), 0x1p1009);

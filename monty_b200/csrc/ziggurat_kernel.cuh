@@ -66,7 +66,13 @@
 namespace mb200 {
 
 constexpr int kZigUnroll = MB200_ZIG_UNROLL;     // hot-loop unrolling (experiments: -DMB200_ZIG_UNROLL=n)
-constexpr int kZigMaxWarps = 20;
+#ifndef MB200_ZIG_MAXWARPS
+#define MB200_ZIG_MAXWARPS 20
+#endif
+#ifndef MB200_ZIG_PITCH
+#define MB200_ZIG_PITCH 35
+#endif
+constexpr int kZigMaxWarps = MB200_ZIG_MAXWARPS;
 // Row pitch of the output tile in elements: 32 slots of the window + pad slots
 // that hold draws banked for the next window (see ziggurat_body).  The pitch is
 // odd for the double tile: the scalar 64-bit stores of a half-warp then fall in
@@ -76,7 +82,7 @@ constexpr int kZigMaxWarps = 20;
 // conflicts) 450 Gdraws/s, 38 doubles (19 warps fit) 460, 34 doubles 457.7, 35 and
 // 37 doubles 465.3 (same box, same day).
 template <typename OutT> struct ZigTile;
-template <> struct ZigTile<double> { static constexpr int PITCH = 35; };
+template <> struct ZigTile<double> { static constexpr int PITCH = MB200_ZIG_PITCH; };
 template <> struct ZigTile<float> { static constexpr int PITCH = 36; };
 constexpr int kZigCopies = 8;                       // replicas of the {x, y} table
 constexpr float kZigBand = 1.0e-4f;                 // |t| below this: decide in double
