@@ -276,3 +276,26 @@ def test_moments_quick(port):                           # test-rng.R:64-112 (red
     assert abs(z.mean()) < 1e-2 and abs(z.var() - 1) < 2e-2
     b = port.sample("binomial", st, 50000, [np.array([100.0]), np.array([0.3])]).ravel()
     assert abs(b.mean() - 30) < 0.1 and abs(b.var() - 21) < 0.5
+
+
+def test_generator_vectors_are_the_reference(reference):
+    """tests/golden/generator_vectors.npz (the reference's samplers on its other generators,
+    what tests/test_gpu_generators.py holds the device-side API to) is what the live reference
+    build produces (tools/make_golden_generators.py)."""
+    import os
+    vec = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generator_vectors.npz"))
+    from cases import sampler_cases
+    n, ns, seed = 48, 6, 20240607
+    for gen, rt in (("xoshiro128plus", "f32"), ("xoshiro128plus", "f64"), ("xoshiro256plus", "f64"),
+                    ("xoroshiro128plusplus", "f64"), ("xoshiro512starstar", "f64")):
+        for name, pars in sampler_cases(n).items():
+            y, st = reference.generator_draw(gen, name, seed, n, ns, pars, rt, jumps=1, long_jumps=1)
+            assert np.array_equal(st, vec["%s/%s/%s/state" % (gen, rt, name)]), (gen, rt, name)
+            assert np.array_equal(y, vec["%s/%s/%s" % (gen, rt, name)], equal_nan=True), (gen, rt, name)
+    # generator<double> on xoshiro256+ through this path equals the bulk path's oracle
+    st0 = reference.seed_states(seed, n)
+    reference.jump(st0, 1)
+    reference.jump(st0, 1, long=True)
+    exp = reference.sample("normal_ziggurat", st0, ns, sampler_cases(n)["normal_ziggurat"])
+    assert np.array_equal(exp, vec["xoshiro256plus/f64/normal_ziggurat"])
+    assert np.array_equal(st0, vec["xoshiro256plus/f64/normal_ziggurat/state"])
