@@ -68,43 +68,76 @@ def algorithmic_bytes(n_streams, n_draws, params, out_bytes):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 2 ms (the
+    timed region of the default run is ~100 ms, one nvidia-smi process start), nvidia-smi
+    as the fallback when the NVML binding is missing."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
-        self.rows = []
+        self.sm, self.mx, self.reasons, self.n = [], [], set(), 0
         self._stop_evt = threading.Event()
+        self.source = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self._nv = None
+            self.source = "nvidia-smi"
 
-    def run(self):
+    def _poll_nvml(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+        self.n += 1
+
+    def _poll_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
+                              "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.split(",")]
+        if r[0].replace(".", "").isdigit():
+            self.sm.append(float(r[0]))
+        if r[1].replace(".", "").isdigit():
+            self.mx.append(float(r[1]))
+        for (name, _), v in zip(self.REASONS, r[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
+        self.n += 1
+
+    def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self._nv is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.002 if self._nv is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for name, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": self.n, "source": self.source}
 
 
 def measured_peak():
