@@ -41,6 +41,24 @@ for n, r in sorted(top):
     st = {k[6:]: int(r[ix[k]]) for k in keys if int(r[ix[k]]) > 0.1 * int(r[ix['# Samples']])}
     print(n, r[ix['Source']].strip()[:58].ljust(58), r[ix['# Samples']].rjust(6), r[ix['Instructions Executed']].rjust(10), st)
 
+# where the executed instructions are: SASS lines grouped by how often they ran (a loop body's
+# lines share one count), heaviest groups first
+from collections import defaultdict
+grp = defaultdict(lambda: [0, 0])
+for r in data:
+    try:
+        e = int(r[ix['Instructions Executed']])
+    except ValueError:
+        continue
+    if e <= 0: continue
+    import math
+    key = round(math.log(e, 1.08))          # counts within 8% of each other
+    grp[key][0] += 1; grp[key][1] += e
+total_exec = sum(v[1] for v in grp.values())
+print("instructions executed (warp level) by execution-count group: total %.4g" % total_exec)
+for key, (nl, ex) in sorted(grp.items(), key=lambda t: -t[1][1])[:14]:
+    print("  ~%.4g executions x %4d SASS lines = %.4g (%.1f%%)" % (ex / nl, nl, ex, 100.0 * ex / total_exec))
+
 # shared-memory / L1 wavefronts per instruction (bank conflicts show up as "excessive")
 wcols = [h for h in hdr if 'avefronts' in h]
 def num(r, h):
