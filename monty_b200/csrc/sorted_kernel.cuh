@@ -32,9 +32,12 @@
 
 namespace mb200 {
 
-#ifndef MB200_SORT_MINBLOCKS
-#define MB200_SORT_MINBLOCKS 3   /* 24 warps per SM at 80 registers: these kernels wait on dependent FP64 chains, occupancy beats the few spills (2: binomial x16 30.7, 3: 35.8, 4: 36.2 but Poisson 46.5 -> 40.0 Gdraws/s) */
-#endif
+// resident CTAs per SM this kernel is compiled for: D::SORT_MINBLOCKS (samplers.cuh), 3 by
+// default -- 24 warps per SM at 80 registers: these kernels wait on dependent FP64 chains,
+// occupancy beats the few spills (2: binomial x16 29.3, 3: 33.9, 4: 33.9 but Poisson x16
+// 45.3 -> 34.9 and hypergeometric 16.4 -> 15.0 Gdraws/s); the negative binomial and beta run
+// at 4 (15.4 -> 16.5, 24.2 -> 24.6), the truncated normal at 2 (29.1 -> 29.8).
+// -DMB200_SORT_MINBLOCKS=n overrides all of them (experiments).
 constexpr int kSortBlock = 256;
 constexpr int kSortTile = 2048;           // streams per tile, kSortTile / kSortBlock per thread
 constexpr int kSortMaxSamples = 64;
@@ -47,7 +50,11 @@ inline size_t sorted_smem_bytes(int n_params, int tables) {
 }
 
 template <class D, typename T, typename OutT>
+#ifdef MB200_SORT_MINBLOCKS
 __global__ void __launch_bounds__(kSortBlock, MB200_SORT_MINBLOCKS)
+#else
+__global__ void __launch_bounds__(kSortBlock, D::SORT_MINBLOCKS)
+#endif
 sorted_sample_kernel(const SampleArgs a) {
   constexpr int NP = D::NP;
   constexpr int PER = kSortTile / kSortBlock;
