@@ -13,7 +13,7 @@ namespace mb200 {
 // log1p, erfc: glibc's s_log1p.c / s_erf.c bit for bit (glibc_math.cuh)
 __device__ __forceinline__ double m_log1p(double x) { return glibc::log1p(x); }
 __device__ __forceinline__ double m_erfc(double x) { return glibc::erfc(x); }
-__device__ __forceinline__ float m_log1p(float x) { return log1pf(x); }
+__device__ __forceinline__ float m_log1p(float x) { return glibc::log1pf(x); }      // s_log1pf.c
 
 template <typename T> __device__ __forceinline__ T maybe_log(T x, bool lg) {   // :33-36
   return lg ? x : m_exp(x);

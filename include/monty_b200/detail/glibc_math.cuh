@@ -151,8 +151,6 @@ GM_FN LogRow logf_row(int i) {
   return LogRow{v.x, v.y};
 }
 GM_FN uint64_t expf_row(int i) { return __ldg(&g_expf_tab[i]); }
-GM_FN float logf_special(float x) { return ::logf(x); }
-GM_FN float expf_special(float x) { return ::expf(x); }
 GM_FN float cosf_large(float x) { return ::cosf(x); }
 GM_FN float tanf_large(float x) { return ::tanf(x); }
 GM_FN float ff_i2f(int k) { return __int2float_rn(k); }
@@ -201,8 +199,6 @@ GM_FN double f_f2d(float x) { return static_cast<double>(x); }
 GM_FN float f_d2f(double x) { volatile float r = static_cast<float>(x); return r; }
 GM_FN LogRow logf_row(int i) { return h_logf_tab[i]; }
 GM_FN uint64_t expf_row(int i) { return h_expf_tab[i]; }
-GM_FN float logf_special(float x) { return __builtin_logf(x); }
-GM_FN float expf_special(float x) { return __builtin_expf(x); }
 GM_FN float cosf_large(float x) { return __builtin_cosf(x); }
 GM_FN float tanf_large(float x) { return __builtin_tanf(x); }
 GM_FN float ff_i2f(int k) { return static_cast<float>(k); }
@@ -1033,11 +1029,16 @@ GM_FN double erfc(double x) {
 // builds, fused operations explicit).  e_lgammaf_r.c is fdlibm's lgamma in float
 // arithmetic (no contraction), with the same structure as lgamma_positive.
 
-// x positive, finite, normal and != 1 handled here; everything else: the platform's logf
+// every argument: subnormals are normalised as in the library, zero / negative / non-finite give IEEE's values
 GM_FN float logf(float x) {
-  const uint32_t ix = ff_bits(x);
+  uint32_t ix = ff_bits(x);
   if (ix == 0x3f800000u) return 0.0f;
-  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) return logf_special(x);
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {      // x < 2^-126, inf or NaN
+    if (ix * 2u == 0) return ff_from_bits(0xff800000u);      // log(+-0) = -inf
+    if (ix == 0x7f800000u) return x;
+    if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) { const float d = ff_sub(x, x); return ff_div(d, d); }
+    ix = ff_bits(ff_mul(x, 0x1p23f)) - (23u << 23);          // subnormal: normalise
+  }
   const uint32_t tmp = ix - 0x3f330000u;
   const int i = static_cast<int>((tmp >> 19) & 15u);
   const int k = static_cast<int32_t>(tmp) >> 23;
@@ -1053,10 +1054,16 @@ GM_FN float logf(float x) {
   return f_d2f(f_fma(r2, y, s));
 }
 
-// |x| < 88 here; larger magnitudes and non-finite arguments: the platform's expf
+// every argument, the over- and underflow thresholds of the library included
 GM_FN float expf(float x) {
   const uint32_t abstop = (ff_bits(x) >> 20) & 0x7ffu;
-  if (abstop > 0x42au) return expf_special(x);
+  if (abstop > 0x42au) {                                     // |x| >= 88 or NaN
+    if (ff_bits(x) == 0xff800000u) return 0.0f;
+    if (abstop >= 0x7f8u) return ff_add(x, x);
+    if (x > 0x1.62e42ep6f) return ff_from_bits(0x7f800000u);        // above log(2^128)
+    if (x < -0x1.9fe368p6f) return 0.0f;                            // below log(2^-150)
+    if (x < -0x1.9d1d9ep6f) return 0x1p-149f;                       // the library's "may underflow" value
+  }
   const double xd = f_f2d(x);
   const double* C = GM_EXPF_POLY;
   const double zs = f_fma(GLIBC_EXPF_INVLN2N, xd, GLIBC_EXPF_SHIFT);
@@ -1181,12 +1188,109 @@ GM_FN float tanf(float x) {
   return kernel_tanf(y0, y1, 1 - ((n & 1) << 1));
 }
 
+// s_log1pf.c (fdlibm's log1p in float arithmetic, Horner polynomial; not an ifunc, nothing
+// fused).  Constants as published: ln2_hi 0x3f317180, ln2_lo 0x3717f7d1, Lp1..Lp7.
+GM_FN float log1pf(float x) {
+  const float ln2_hi = ff_from_bits(0x3f317180u), ln2_lo = ff_from_bits(0x3717f7d1u);
+  const float Lp1 = ff_from_bits(0x3f2aaaabu), Lp2 = ff_from_bits(0x3ecccccdu), Lp3 = ff_from_bits(0x3e924925u),
+              Lp4 = ff_from_bits(0x3e638e29u), Lp5 = ff_from_bits(0x3e3a3325u), Lp6 = ff_from_bits(0x3e1cd04fu),
+              Lp7 = ff_from_bits(0x3e178897u);
+  const int32_t hx = static_cast<int32_t>(ff_bits(x));
+  const int32_t ax = hx & 0x7fffffff;
+  int k = 1;
+  int32_t hu = 1;
+  float f = x, c = 0.0f;
+  if (hx < 0x3ed413d7) {                                    // x < 0.41422
+    if (ax >= 0x3f800000) {                                 // x <= -1
+      if (x == -1.0f) return ff_div(-0x1p25f, 0.0f);
+      const float d = ff_sub(x, x);
+      return ff_div(d, d);
+    }
+    if (ax < 0x31000000) {                                  // |x| < 2^-29
+      if (ax < 0x24800000) return x;
+      return ff_sub(x, ff_mul(ff_mul(x, x), 0.5f));
+    }
+    if (hx > 0 || hx <= static_cast<int32_t>(0xbe95f61fu)) k = 0;
+  } else if (hx >= 0x7f800000) {
+    return ff_add(x, x);
+  }
+  if (k != 0) {
+    float u;
+    if (hx < 0x5a000000) {
+      u = ff_add(1.0f, x);
+      hu = static_cast<int32_t>(ff_bits(u));
+      k = (hu >> 23) - 127;
+      c = (k > 0) ? ff_sub(1.0f, ff_sub(u, x)) : ff_sub(x, ff_sub(u, 1.0f));
+      c = ff_div(c, u);
+    } else {
+      u = x;
+      hu = hx;
+      k = (hu >> 23) - 127;
+    }
+    hu &= 0x007fffff;
+    if (hu < 0x3504f7) {
+      u = ff_from_bits(static_cast<uint32_t>(hu) | 0x3f800000u);
+    } else {
+      k += 1;
+      u = ff_from_bits(static_cast<uint32_t>(hu) | 0x3f000000u);
+      hu = (0x00800000 - hu) >> 2;
+    }
+    f = ff_sub(u, 1.0f);
+  }
+  const float hfsq = ff_mul(ff_mul(0.5f, f), f);
+  const float kf = ff_i2f(k);
+  if (hu == 0) {                                            // |f| < 2^-20
+    if (f == 0.0f) {
+      if (k == 0) return 0.0f;
+      return ff_add(ff_add(ff_mul(kf, ln2_lo), c), ff_mul(kf, ln2_hi));
+    }
+    const float R = ff_mul(hfsq, ff_sub(1.0f, ff_mul(Lp1, f)));
+    if (k == 0) return ff_sub(f, R);
+    return ff_sub(ff_mul(kf, ln2_hi), ff_sub(ff_sub(R, ff_add(ff_mul(kf, ln2_lo), c)), f));
+  }
+  const float s = ff_div(f, ff_add(2.0f, f));
+  const float z = ff_mul(s, s);
+  float R = ff_add(ff_mul(Lp7, z), Lp6);
+  R = ff_add(ff_mul(R, z), Lp5);
+  R = ff_add(ff_mul(R, z), Lp4);
+  R = ff_add(ff_mul(R, z), Lp3);
+  R = ff_add(ff_mul(R, z), Lp2);
+  R = ff_add(ff_mul(R, z), Lp1);
+  R = ff_mul(R, z);
+  const float t = ff_mul(ff_add(R, hfsq), s);
+  if (k == 0) return ff_sub(f, ff_sub(hfsq, t));
+  const float e = ff_add(ff_add(ff_mul(kf, ln2_lo), c), t);
+  return ff_sub(ff_mul(kf, ln2_hi), ff_sub(ff_sub(hfsq, e), f));
+}
+
 // e_powf.c: log2(x) in double from a 16-row table and a degree-5 polynomial, y log2(x),
 // exp2 by exp2f's table.  x positive and normal, y finite and non-zero, |y log2 x| < 126
 // here; everything else: the platform's powf.
+// checkint() of e_powf.c: 0 = y is not an integer, 1 = odd, 2 = even
+GM_FN int powf_checkint(uint32_t iy) {
+  const int e = static_cast<int>(iy >> 23) & 0xff;
+  if (e < 0x7f) return 0;
+  if (e > 0x7f + 23) return 2;
+  if (iy & ((1u << (0x7f + 23 - e)) - 1)) return 0;
+  if (iy & (1u << (0x7f + 23 - e))) return 1;
+  return 2;
+}
+
 GM_FN float powf(float x, float y) {
-  const uint32_t ix = ff_bits(x), iy = ff_bits(y);
-  if (ix - 0x00800000u > 0x7effffffu || 2u * iy - 1u > 0xfefffffeu) return powf_special(x, y);
+  uint32_t ix = ff_bits(x);
+  const uint32_t iy = ff_bits(y);
+  bool negate = false;
+  if (ix - 0x00800000u > 0x7effffffu || 2u * iy - 1u > 0xfefffffeu) {
+    // zero / infinite / NaN operands: IEEE-defined results, the platform's powf
+    if (2u * iy - 1u > 0xfefffffeu || 2u * ix - 1u > 0xfefffffeu) return powf_special(x, y);
+    if (ix & 0x80000000u) {                                  // finite x < 0: integer y only
+      const int yint = powf_checkint(iy);
+      if (yint == 0) { const float d = ff_sub(x, x); return ff_div(d, d); }
+      negate = yint == 1;
+      ix &= 0x7fffffffu;
+    }
+    if (ix < 0x00800000u) ix = (ff_bits(ff_mul(ff_from_bits(ix), 0x1p23f)) & 0x7fffffffu) - (23u << 23);   // subnormal: normalise
+  }
   const double* A = GM_POWF_POLY;
   const uint32_t tmp = ix - 0x3f330000u;
   const int i = static_cast<int>((tmp >> 19) & 15u);
@@ -1204,7 +1308,11 @@ GM_FN float powf(float x, float y) {
   q = f_fma(r2, p, q);
   ya = f_fma(ya, r4, q);
   const double ylogx = f_mul(f_f2d(y), ya);
-  if (((f_bits(ylogx) >> 47) & 0xffffu) > 0x80beu) return powf_special(x, y);      // |y log2 x| >= 126 (scaled) or negative large
+  if (((f_bits(ylogx) >> 47) & 0xffffu) > 0x80beu) {         // |y log2 x| >= 126
+    if (ylogx > 0x1.fffffffd1d571p+6) return ff_from_bits(negate ? 0xff800000u : 0x7f800000u);
+    if (ylogx <= -150.0) return ff_from_bits(negate ? 0x80000000u : 0u);
+    if (ylogx < -149.0) return ff_from_bits(negate ? 0x80000001u : 0x00000001u);          // the library's "may underflow" value
+  }
   const double* C = GM_EXP2F_POLY;
   const double kd0 = f_add(ylogx, GLIBC_EXP2F_SHIFT_SCALED);
   const uint64_t ki = f_bits(kd0);
@@ -1215,7 +1323,8 @@ GM_FN float powf(float x, float y) {
   const double rr2 = f_mul(rr, rr);
   double yy = f_fma(rr, C[2], 1.0);
   yy = f_fma(zz, rr2, yy);
-  return f_d2f(f_mul(yy, s));
+  const float res = f_d2f(f_mul(yy, s));
+  return negate ? ff_from_bits(ff_bits(res) ^ 0x80000000u) : res;
 }
 
 GM_FN float lgammaf_2_to_8(float x) {

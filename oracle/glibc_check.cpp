@@ -155,7 +155,7 @@ extern "C" int64_t gm_compare_lgamma_batch(uint64_t seed, int64_t n) {
   return mism;
 }
 // The float routines, EXHAUSTIVELY: every float bit pattern in [lo_bits, hi_bits) through
-// fn 0 = logf, 1 = expf, 2 = cosf, 4 = tanf, 3 = lgammaf (positive finite arguments only) against the
+// fn 0 = logf, 1 = expf, 2 = cosf, 4 = tanf, 5 = log1pf, 3 = lgammaf (positive finite arguments only) against the
 // live libm; returns the number of differing results, *bad = the first offender's bits.
 extern "C" int64_t gm_compare_float(int fn, uint32_t lo_bits, uint32_t hi_bits, uint32_t* bad) {
   int64_t mism = 0;
@@ -171,6 +171,7 @@ extern "C" int64_t gm_compare_float(int fn, uint32_t lo_bits, uint32_t hi_bits, 
       case 1: got = mb200::glibc::expf(x); want = ::expf(x); break;
       case 2: got = mb200::glibc::cosf(x); want = ::cosf(x); break;
       case 4: got = mb200::glibc::tanf(x); want = ::tanf(x); break;
+      case 5: got = mb200::glibc::log1pf(x); want = ::log1pf(x); break;
       default: got = mb200::glibc::lgammaf_positive(x); want = ::lgammaf_r(x, &sg); break;
     }
     uint32_t gb, wb;
@@ -198,10 +199,17 @@ extern "C" int64_t gm_compare_powf(uint64_t seed, int64_t n, int mode) {
       if (mode == 0) {
         x = static_cast<float>(xb >> 8) * 0x1p-24f + 0x1p-25f;
         y = 0.05f + 20.0f * (static_cast<float>(yb >> 8) * 0x1p-24f);
-      } else {
+      } else if (mode == 1) {
         xb &= 0x7fffffffu;
         std::memcpy(&x, &xb, 4);
         std::memcpy(&y, &yb, 4);
+      } else if (mode == 2) {                     // any x, small integer or any y: negative bases, subnormals
+        std::memcpy(&x, &xb, 4);
+        if (yb & 1) y = static_cast<float>(static_cast<int>((yb >> 8) % 41) - 20); else std::memcpy(&y, &yb, 4);
+      } else {                                    // results next to over- and underflow: x^y with |y log2 x| in (120, 155)
+        x = 0.5f + static_cast<float>(xb >> 8) * 0x1p-24f * 1.5f;
+        const float t = 120.0f + 35.0f * (static_cast<float>(yb >> 8) * 0x1p-24f);
+        y = ((yb & 1) ? t : -t) / std::log2(x);
       }
       const float got = mb200::glibc::powf(x, y), want = ::powf(x, y);
       uint32_t gb, wb;

@@ -95,9 +95,9 @@ FLOAT_STRIDE = int(os.environ.get("MONTY_B200_GLIBC_FLOAT_STRIDE", "16"))
 
 @pytest.mark.parametrize("fn,name,lo,hi", [(0, "logf", 0, 0xFFFFFFFF), (1, "expf", 0, 0xFFFFFFFF),
                                           (2, "cosf", 0, 0xFF800000), (3, "lgammaf", 1, 0x7F800000),
-                                          (4, "tanf", 0, 0xFF800000)])
+                                          (4, "tanf", 0, 0xFF800000), (5, "log1pf", 0, 0xFF800001)])
 def test_float_routines_same_bits_as_libm(gm, fn, name, lo, hi):
-    """real_type = float: logf / expf / cosf / lgammaf / tanf over the float bit patterns
+    """real_type = float: logf / expf / cosf / lgammaf / tanf / log1pf over the float bit patterns
     (blocks of 2^20 patterns, every FLOAT_STRIDE-th block)."""
     bad = ctypes.c_uint32(0)
     block = 1 << 20
@@ -112,6 +112,8 @@ def test_float_routines_same_bits_as_libm(gm, fn, name, lo, hi):
 def test_powf_and_the_batched_forms(gm):
     assert gm.gm_compare_powf(5, N, 0) == 0          # powf(uniform float, (0.05, 20))
     assert gm.gm_compare_powf(6, N, 1) == 0          # powf(any positive float, any float)
+    assert gm.gm_compare_powf(8, N, 2) == 0          # powf(any float, small integers / any float): negative bases, subnormals
+    assert gm.gm_compare_powf(9, N, 3) == 0          # results next to over- and underflow
     assert gm.gm_compare_log_batch(7, N // 4) == 0   # log_positive_normal_batch<4> == four calls
     assert gm.gm_compare_lgamma_batch(3, N // 6) == 0
 

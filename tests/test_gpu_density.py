@@ -51,11 +51,21 @@ def test_float_variant(mb, oracle):
     got = mb.density.density_negative_binomial_mu(x, pars[0], pars[1], True, is_float=True)
     exp = oracle.density("negative_binomial_mu", x, pars, True, "f32")
     assert np.allclose(got, exp, rtol=2e-4, atol=2e-4)
-    # logf / lgammaf are glibc's bits: identical outside the large-size limit, whose log1pf is the toolkit's
-    size, mu = (np.broadcast_to(np.asarray(p, dtype=np.float32), np.shape(x)) for p in pars)
-    limit = mu < np.float32(np.finfo(np.float32).eps * 100) * size
-    same = (got == exp) | (np.isnan(got) & np.isnan(exp))
-    assert same[~limit].all(), float(1 - same[~limit].mean())
+    same = (got == exp) | (np.isnan(got) & np.isnan(exp))          # logf / lgammaf / log1pf are glibc's bits
+    assert same.all(), float(1 - same.mean())
+
+
+@pytest.mark.parametrize("name", sorted(density_cases(4)))
+def test_float_parity(mb, oracle, name):
+    """real_type = float (the reference's `<float>` instantiations of density.hpp): logf, expf,
+    powf, lgammaf, log1pf return glibc's bits on the device, so the float densities are
+    bit-identical as well, in log and in non-log form."""
+    x, pars = density_cases(20000)[name]
+    for log in (True, False):
+        got = gpu_density(mb, name, x, pars, log, "f32")
+        exp = oracle.density(name, x, pars, log, "f32")
+        same = (got == exp) | (np.isnan(got) & np.isnan(exp))
+        assert same.all(), (name, log, float(1 - same.mean()), got[~same][:3], exp[~same][:3])
 
 
 def test_known_answers_against_scipy(mb):
