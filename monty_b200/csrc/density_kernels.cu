@@ -260,7 +260,11 @@ __device__ __forceinline__ void density_compute4(const T (&x)[4], const T (&p)[N
 }
 
 template <int DENS, typename T>
+#ifdef MB200_DENS_TILE_MINBLOCKS          /* occupancy experiments */
+__global__ void __launch_bounds__(kDensBlock, MB200_DENS_TILE_MINBLOCKS)
+#else
 __global__ void __launch_bounds__(kDensBlock)
+#endif
 density_tile_kernel(const DensityArgs a, const unsigned long long n_full_tiles) {
   using Cn = DensCanon<DENS>;
   constexpr int NPD = DensNP<DENS>::value;
