@@ -215,6 +215,17 @@ GM_FN float powf_special(float x, float y) { return __builtin_powf(x, y); }
 #define GM_LOG_POLY h_log_poly
 #define GM_LOG_POLY1 h_log_poly1
 #endif
+// the two 32-bit words of a double: the exponent arithmetic of log needs the high one only
+// (the constants it subtracts have a zero low word), which halves its integer instructions
+#if defined(__CUDA_ARCH__)
+GM_FN uint32_t f_hi(double x) { return static_cast<uint32_t>(__double2hiint(x)); }
+GM_FN uint32_t f_lo(double x) { return static_cast<uint32_t>(__double2loint(x)); }
+GM_FN double f_from_hilo(uint32_t hi, uint32_t lo) { return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo)); }
+#else
+GM_FN uint32_t f_hi(double x) { return static_cast<uint32_t>(f_bits(x) >> 32); }
+GM_FN uint32_t f_lo(double x) { return static_cast<uint32_t>(f_bits(x)); }
+GM_FN double f_from_hilo(uint32_t hi, uint32_t lo) { return f_from_bits((static_cast<uint64_t>(hi) << 32) | lo); }
+#endif
 GM_FN double f_abs(double x) { return f_from_bits(f_bits(x) & 0x7fffffffffffffffull); }
 GM_FN double f_neg(double x) { return f_from_bits(f_bits(x) ^ 0x8000000000000000ull); }
 
@@ -260,12 +271,14 @@ GM_FN double log_near_one(double x) {
 }
 
 // Positive, finite, normal x outside the window around 1 (the caller checks).
-GM_FN double log_main(uint64_t ix) {
+// (xh, xl) = the words of x.  e_log.c: tmp = ix - OFF; i = (tmp >> 45) % 128; k = tmp >> 52;
+// iz = ix - (tmp & 0xfff << 52) -- OFF has a zero low word, so all of it happens in the high word
+GM_FN double log_main(uint32_t xh, uint32_t xl) {
   const double* A = GM_LOG_POLY;
-  const uint64_t tmp = ix - kLogOff;
-  const int i = static_cast<int>((tmp >> 45) & 127);
-  const int k = static_cast<int>(static_cast<int64_t>(tmp) >> 52);
-  const double z = f_from_bits(ix - (tmp & 0xfff0000000000000ull));
+  const uint32_t th = xh - static_cast<uint32_t>(kLogOff >> 32);
+  const int i = static_cast<int>((th >> 13) & 127u);
+  const int k = static_cast<int32_t>(th) >> 20;
+  const double z = f_from_hilo(xh - (th & 0xfff00000u), xl);
   const LogRow row = log_row(i);
   const double kd = f_i2d(k);
   const double w = f_fma(kd, GLIBC_LOG_LN2HI, row.logc);
@@ -283,9 +296,14 @@ GM_FN double log_main(uint64_t ix) {
 }
 
 // log(x) for every double (special cases as e_log.c, without errno).
+// the window [1 - 2^-4, 1 + 0x1.09p-4): both of its ends have a zero low word
+GM_FN bool log_is_near_one(uint32_t hi) {
+  return hi - static_cast<uint32_t>(kLogNearLo >> 32) < static_cast<uint32_t>(kLogNearSpan >> 32);
+}
+
 GM_FN double log(double x) {
   uint64_t ix = f_bits(x);
-  if (ix - kLogNearLo < kLogNearSpan) return log_near_one(x);
+  if (log_is_near_one(static_cast<uint32_t>(ix >> 32))) return log_near_one(x);
   const uint32_t top = static_cast<uint32_t>(ix >> 48);
   if (top - 0x0010u >= 0x7ff0u - 0x0010u) {
     if (ix * 2 == 0) return f_from_bits(0xfff0000000000000ull);                  // log(+-0) = -inf
@@ -296,15 +314,15 @@ GM_FN double log(double x) {
     ix = f_bits(f_mul(x, 0x1p52));                                               // subnormal
     ix -= 52ull << 52;
   }
-  return log_main(ix);
+  return log_main(static_cast<uint32_t>(ix >> 32), static_cast<uint32_t>(ix));
 }
 
 // log of a positive, finite, normal number (a random_real() output, a ratio of
 // positive normals ...): no special-case test.
 GM_FN double log_positive_normal(double x) {
-  const uint64_t ix = f_bits(x);
-  if (ix - kLogNearLo < kLogNearSpan) return log_near_one(x);
-  return log_main(ix);
+  const uint32_t hi = f_hi(x);
+  if (log_is_near_one(hi)) return log_near_one(x);
+  return log_main(hi, f_lo(x));
 }
 
 // N logs of positive, finite, normal numbers at once.  The window around 1
@@ -322,9 +340,9 @@ GM_FN void log_positive_normal_batch(const double (&x)[N], double (&lg)[N]) {
 #pragma unroll
 #endif
   for (int i = 0; i < N; ++i) {
-    const uint64_t ix = f_bits(x[i]);
-    if (ix - kLogNearLo < kLogNearSpan) pend |= 1u << i;
-    lg[i] = log_main(ix);
+    const uint32_t hi = f_hi(x[i]);
+    if (log_is_near_one(hi)) pend |= 1u << i;
+    lg[i] = log_main(hi, f_lo(x[i]));
   }
   while (pend) {
     const unsigned low = pend & (0u - pend);
@@ -548,7 +566,7 @@ GM_FN double lgamma_2_to_8(double x) {
 
 // 8 <= x < 2^58: (x - 1/2)(log x - 1) + w(1 / x)
 GM_FN double lgamma_stirling(double x) {
-  const double t = log_main(f_bits(x));         // x >= 8: log()'s main path, no window, no special case
+  const double t = log_main(f_hi(x), f_lo(x));  // x >= 8: log()'s main path, no window, no special case
   const double z = f_div(1.0, x);
   const double y = f_mul(z, z);
   double w = f_add(GLIBC_LG_W5, f_mul(y, GLIBC_LG_W6));

@@ -230,15 +230,29 @@ __device__ __forceinline__ void density_compute4(const T (&x)[4], const T (&p)[N
   if constexpr (DENS == MB200_DENS_POISSON && sizeof(T) == 8) {
     double lgm[4], ll[4];
     bool plain = true;
+    if (xi != nullptr && lgt != nullptr) {
+      // branch-free look-ups (clamped index); the rare observation beyond the table is
+      // patched afterwards
+      bool beyond = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned i = static_cast<unsigned>(xi[u]);
+        beyond = beyond || i >= static_cast<unsigned>(kLgtN - 1);
+        lgm[u] = __ldg(lgt + (i < static_cast<unsigned>(kLgtN - 1) ? i : 0u) + 1);      // the bits m_lgamma(x + 1) returns (same table)
+      }
+      if (beyond) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (static_cast<unsigned>(xi[u]) >= static_cast<unsigned>(kLgtN - 1)) lgm[u] = m_lgamma(x[u] + 1);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) lgm[u] = m_lgamma(x[u] + 1);
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (xi != nullptr && lgt != nullptr && static_cast<unsigned>(xi[u]) < static_cast<unsigned>(kLgtN - 1)) {
-        lgm[u] = __ldg(lgt + xi[u] + 1);            // the bits m_lgamma(x + 1) returns (same table)
-      } else {
-        lgm[u] = m_lgamma(x[u] + 1);
-      }
-      const uint64_t ix = glibc::f_bits(p[0][u]);
-      plain = plain && (ix - 0x0010000000000000ull < 0x7fe0000000000000ull);      // positive, finite, normal
+      plain = plain && (glibc::f_hi(p[0][u]) - 0x00100000u < 0x7fe00000u);        // positive, finite, normal
     }
     if (plain) {
       double lam[4] = {p[0][0], p[0][1], p[0][2], p[0][3]};
