@@ -33,6 +33,13 @@ int mb200_example_generator_draw(int gen, int dist, int real_type, uint64_t seed
                                  const double* const* params_host, const size_t* param_len,
                                  double* out_host, void* state_out);
 
+/* monty_b200::device_prng<G>(n_streams, seed words) -- the reference's seed-vector constructor
+ * (prng.hpp:38-53) -- exported; with reimport_and_jump the states are imported into a second
+ * container, jumped once and exported from there.  gen: XOSHIRO128PLUS (uint32 words),
+ * XOSHIRO256PLUS, XOROSHIRO128PLUSPLUS, XOSHIRO512STARSTAR (uint64 words). */
+int mb200_example_generator_seed_vector(int gen, const void* words, size_t n_words, size_t n_streams,
+                                        int reimport_and_jump, void* state_out);
+
 /* Bootstrap particle filter of the stochastic SIR model of the reference's
  * test-suite (tests/testthat/helper-sir-filter.R:56-117): n_particles =
  * n_streams of `system`, one stream in `filter` for the systematic

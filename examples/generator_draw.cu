@@ -116,3 +116,43 @@ extern "C" int mb200_example_generator_draw(int gen, int dist, int real_type, ui
   if (a.out) cudaFree(a.out);
   return rc;
 }
+
+// device_prng<G>(n, seed_words): the reference's seed-vector constructor (hdr/prng.hpp:38-53: as
+// many full states as the words give, the rest by jump() from the last one), then optionally
+// import_state() of the exported states into a second container and one jump() there --
+// export / import round trip.  words: n_words values of the generator's int_type (uint32 for
+// xoshiro128, uint64 otherwise); state_out: int_type[n_streams][state words].
+namespace {
+template <class G>
+int seed_vector_run(const void* words, size_t n_words, size_t n_streams, int reimport_and_jump, void* state_out) {
+  using W = typename G::int_type;
+  try {
+    std::vector<W> seed(static_cast<const W*>(words), static_cast<const W*>(words) + n_words);
+    monty_b200::device_prng<G> a(n_streams, seed);
+    std::vector<W> st = a.export_state();
+    if (reimport_and_jump) {
+      monty_b200::device_prng<G> b(n_streams, static_cast<uint64_t>(1));
+      b.import_state(st);
+      b.jump();
+      st = b.export_state();
+    }
+    std::memcpy(state_out, st.data(), st.size() * sizeof(W));
+    return MB200_OK;
+  } catch (const std::exception&) {
+    return MB200_ERR_ARG;
+  }
+}
+}  // namespace
+
+extern "C" int mb200_example_generator_seed_vector(int gen, const void* words, size_t n_words, size_t n_streams,
+                                                   int reimport_and_jump, void* state_out) {
+  namespace mr = monty::random;
+  if (!words || !state_out || n_streams == 0) return MB200_ERR_ARG;
+  switch (gen) {
+  case MB200_GEN_XOSHIRO128PLUS: return seed_vector_run<mr::xoshiro128plus>(words, n_words, n_streams, reimport_and_jump, state_out);
+  case MB200_GEN_XOSHIRO256PLUS: return seed_vector_run<mr::xoshiro256plus>(words, n_words, n_streams, reimport_and_jump, state_out);
+  case MB200_GEN_XOROSHIRO128PLUSPLUS: return seed_vector_run<mr::xoroshiro128plusplus>(words, n_words, n_streams, reimport_and_jump, state_out);
+  case MB200_GEN_XOSHIRO512STARSTAR: return seed_vector_run<mr::xoshiro512starstar>(words, n_words, n_streams, reimport_and_jump, state_out);
+  default: return MB200_ERR_ARG;
+  }
+}

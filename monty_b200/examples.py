@@ -17,6 +17,7 @@ lib.mb200_example_inline_draw.restype = C.c_int
 lib.mb200_example_sir_filter.restype = C.c_int
 lib.mb200_example_math_probe.restype = C.c_int
 lib.mb200_example_generator_draw.restype = C.c_int
+lib.mb200_example_generator_seed_vector.restype = C.c_int
 
 lib.mb200_example_inline_multinomial.restype = C.c_int
 
@@ -121,3 +122,15 @@ def generator_draw(gen, dist, seed, n_streams, n_samples, params=(), real_type="
         C.c_uint64(seed), C.c_size_t(n_streams), C.c_size_t(n_samples), C.c_int(jumps), C.c_int(long_jumps),
         ptrs, lens, out.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
     return out, st
+
+
+def generator_seed_vector(gen, words, n_streams, reimport_and_jump=False):
+    """monty_b200::device_prng<gen>(n_streams, seed words): the reference's seed-vector
+    constructor; optionally export -> import into a second container -> jump -> export."""
+    n_words, wt = generator_layout(gen)
+    w = np.ascontiguousarray(words, dtype=wt)
+    st = np.empty((n_streams, n_words), dtype=wt)
+    check(lib.mb200_example_generator_seed_vector(C.c_int(GENERATORS.index(gen)), w.ctypes.data_as(C.c_void_p),
+                                                  C.c_size_t(w.size), C.c_size_t(n_streams),
+                                                  C.c_int(1 if reimport_and_jump else 0), st.ctypes.data_as(C.c_void_p)))
+    return st

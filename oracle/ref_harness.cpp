@@ -265,9 +265,42 @@ int generator_draw_impl(int dist, uint64_t seed, size_t n_streams, size_t n_samp
   return 0;
 }
 
+// prng<G>(n, seed vector) [-> export -> import into another prng -> jump] -> export
+// ref: hdr/prng.hpp:38-53, 92-122
+template <typename G>
+int seed_vector_impl(const void* words, size_t n_words, size_t n_streams, int reimport_and_jump, void* state_out) {
+  using W = typename G::int_type;
+  std::vector<W> seed(static_cast<const W*>(words), static_cast<const W*>(words) + n_words);
+  mr::prng<G> a(n_streams, seed, false);
+  std::vector<W> st = a.export_state();
+  if (reimport_and_jump) {
+    mr::prng<G> b(n_streams, 1, false);
+    b.import_state(st);
+    b.jump();
+    st = b.export_state();
+  }
+  std::memcpy(state_out, st.data(), st.size() * sizeof(W));
+  return 0;
+}
+
 extern "C" {
 
 const char* ref_last_error(void) { return g_err.c_str(); }
+
+int ref_generator_seed_vector(int gen, const void* words, size_t n_words, size_t n_streams,
+                              int reimport_and_jump, void* state_out) {
+  try {
+    switch (gen) {
+    case MB200_GEN_XOSHIRO128PLUS: return seed_vector_impl<mr::xoshiro128plus>(words, n_words, n_streams, reimport_and_jump, state_out);
+    case MB200_GEN_XOSHIRO256PLUS: return seed_vector_impl<mr::xoshiro256plus>(words, n_words, n_streams, reimport_and_jump, state_out);
+    case MB200_GEN_XOROSHIRO128PLUSPLUS: return seed_vector_impl<mr::xoroshiro128plusplus>(words, n_words, n_streams, reimport_and_jump, state_out);
+    case MB200_GEN_XOSHIRO512STARSTAR: return seed_vector_impl<mr::xoshiro512starstar>(words, n_words, n_streams, reimport_and_jump, state_out);
+    default: break;
+    }
+  } catch (const std::exception& e) { g_err = e.what(); return -3; }
+  g_err = "unsupported generator";
+  return -2;
+}
 
 // the reference's samplers instantiated on its other generators (default for float:
 // xoshiro128+, hdr/random.hpp:31-47); mirrors examples/generator_draw.cu

@@ -184,6 +184,24 @@ class Oracle:
             raise OracleError(self._err())
         return out, st
 
+    def generator_seed_vector(self, gen, words, n_streams, reimport_and_jump=False):
+        """prng<gen>(n_streams, seed vector) [-> export -> import -> jump] -> export (reference build only)."""
+        fam = gen
+        for scr in ("plusplus", "starstar", "plus"):
+            if gen.endswith(scr):
+                fam = gen[:-len(scr)]
+                break
+        n_words, wt = {"xoshiro256": (4, np.uint64), "xoshiro128": (4, np.uint32),
+                       "xoroshiro128": (2, np.uint64), "xoshiro512": (8, np.uint64)}[fam]
+        w = np.ascontiguousarray(words, dtype=wt)
+        st = np.zeros((n_streams, n_words), dtype=wt)
+        rc = self._fn("generator_seed_vector")(C.c_int(GEN_NAMES.index(gen)), w.ctypes.data_as(C.c_void_p),
+                                               C.c_size_t(w.size), C.c_size_t(n_streams),
+                                               C.c_int(1 if reimport_and_jump else 0), st.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise OracleError(self._err())
+        return st
+
     def sir_filter(self, system_state, filter_state, pars, data_time, data_incidence, resample=True):
         """The SIR particle filter of the reference's test-suite over the
         reference's C++ samplers (oracle/ref_harness.cpp, reference kind only).

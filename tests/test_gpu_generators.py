@@ -76,6 +76,21 @@ def test_seeding_and_jumps(ex, reference, gen, rt):
         assert np.array_equal(st, est), (gen, jumps, long_jumps)
 
 
+@pytest.mark.parametrize("gen", ["xoshiro128plus", "xoshiro256plus", "xoroshiro128plusplus", "xoshiro512starstar"])
+def test_seed_vector_export_import(ex, reference, gen):
+    """device_prng<G>(n, seed words): full states from the words while they last, then jump()
+    from the last one (hdr/prng.hpp:38-53); export_state -> import_state into a second
+    container -> jump -> export_state (hdr/prng.hpp:92-122)."""
+    n_words, wt = ex.generator_layout(gen)
+    rs = np.random.default_rng(5)
+    for n_states, n_streams in ((1, 9), (3, 9), (9, 9), (12, 9)):
+        words = rs.integers(1, np.iinfo(wt).max, n_states * n_words, dtype=wt)
+        for rj in (False, True):
+            got = ex.generator_seed_vector(gen, words, n_streams, rj)
+            exp = reference.generator_seed_vector(gen, words, n_streams, rj)
+            assert np.array_equal(got, exp), (gen, n_states, rj)
+
+
 def test_default_generators(ex, vectors):
     """generator<float> is xoshiro128+ (16-byte states), generator<double> xoshiro256+."""
     _, st = ex.generator_draw("xoshiro128plus", "real", 1, 3, 1, [], "f32")
