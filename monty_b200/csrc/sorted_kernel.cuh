@@ -42,6 +42,12 @@ constexpr int kSortBlock = 256;
 constexpr int kSortTile = 2048;           // streams per tile, kSortTile / kSortBlock per thread
 constexpr int kSortMaxSamples = 64;
 constexpr int kSortKeys = 16;             // regime keys 0..14, 15 = stream does not exist
+// free lanes at which a warp of the persistent variant takes new streams (measured 8 / 16 / 24:
+// binomial x 1 14.6 / 14.5 / 14.4, Poisson x 1 20.4 / 20.4 / 20.1, truncated normal x 16 38.4 / 37.8 / 36.1)
+#ifndef MB200_SORT_REFILL
+#define MB200_SORT_REFILL 8
+#endif
+constexpr int kSortRefill = MB200_SORT_REFILL;
 
 inline size_t sorted_smem_bytes(int n_params, int tables) {
   size_t b = sizeof(double) * kSortTile * (n_params > 0 ? n_params : 1);
@@ -49,11 +55,15 @@ inline size_t sorted_smem_bytes(int n_params, int tables) {
   return b;
 }
 
-template <class D, typename T, typename OutT>
+// PERSIST (DEFER samplers only): lanes keep working across 32-stream chunk boundaries, see
+// step 3.  Chosen per launch (launch_sorted_t): it wins where streams finish at very
+// different times (one draw per stream; the truncated normal's tail rejections) and loses
+// ~10% on long regular batches, where each refill stalls the warp on the new streams' loads.
+template <class D, typename T, typename OutT, bool PERSIST>
 #ifdef MB200_SORT_MINBLOCKS
 __global__ void __launch_bounds__(kSortBlock, MB200_SORT_MINBLOCKS)
 #else
-__global__ void __launch_bounds__(kSortBlock, D::SORT_MINBLOCKS)
+__global__ void __launch_bounds__(kSortBlock, PERSIST ? 3 : D::SORT_MINBLOCKS)
 #endif
 sorted_sample_kernel(const SampleArgs a) {
   constexpr int NP = D::NP;
@@ -125,6 +135,95 @@ sorted_sample_kernel(const SampleArgs a) {
     //    cost of a chunk varies by an order of magnitude between regimes, and
     //    with a static assignment the cheap warps would wait at the barrier
     //    below for the expensive ones
+    if constexpr (PERSIST) {
+      // Persistent lanes.  A lane keeps its stream until the stream's n draws are made; when
+      // at least half of the warp's lanes are free, the free lanes take the next streams of
+      // the order TOGETHER (their prepare() runs with >= 16 lanes) -- so a warp does not
+      // wait for the slowest of 32 streams before it starts the next 32 (n = 1: a third of
+      // the lanes needed a second or third attempt while the others idled).
+      // Rejection loop with the expensive accept test deferred: a lane whose candidate
+      // fails the cheap squeeze parks it; the parked candidates of the warp are tested
+      // together once half the warp waits (or nobody can run), so the ~250-instruction
+      // test executes with many lanes active.  Per stream nothing changes: same words,
+      // same operations.
+      const unsigned lane = tid & 31;
+      const unsigned lt_mask = (1u << lane) - 1u;
+      bool have = false, parked = false, more = true;
+      unsigned d = 0;
+      unsigned long long stream = 0;
+      OutT* row = out;
+      typename D::Prep prep;
+      typename D::Cand cand;
+      Rng rng;
+#pragma unroll 1
+      for (;;) {
+        const unsigned m_have = __ballot_sync(0xffffffffu, have);
+        if (more && __popc(m_have) <= 32 - kSortRefill) {
+          const unsigned m_free = ~m_have;
+          const unsigned want = static_cast<unsigned>(__popc(m_free));
+          unsigned first = 0;
+          if (lane == 0) first = atomicAdd(&s_chunk, want);
+          first = __shfl_sync(0xffffffffu, first, 0);
+          if (first + want >= count) more = false;
+          const unsigned k = first + static_cast<unsigned>(__popc(m_free & lt_mask));
+          if (!have && k < count) {
+            const unsigned j = s_order[count - 1 - k];
+            stream = base + j;
+            row = out + stream * n;
+            T par[NP > 0 ? NP : 1];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) par[q] = static_cast<T>(par_s[q * kSortTile + j]);
+            const int e = D::prepare(par, prep, ctx);
+            if (e != kOk) {
+              report_error(a.err, stream, e, nullptr);
+              for (unsigned q = 0; q < n; ++q) row[q] = out_nan<OutT>();
+            } else {
+              rng.s = load_state(a.state, stream);
+              have = true;
+              parked = false;
+              d = 0;
+            }
+          }
+        }
+        const bool run = have && !parked;
+        const unsigned m_run = __ballot_sync(0xffffffffu, run);
+        unsigned m_park = __ballot_sync(0xffffffffu, parked);
+        if ((m_run | m_park) == 0) {
+          if (!more) break;
+          continue;                                   // nothing in hand, streams left: refill
+        }
+        if (run) {
+          T value;
+          const int st = D::attempt(rng, prep, ctx, cand, value);
+          if (D::DYN_ERR && ctx.err) {
+            // a data-dependent failure inside a composition: the stream is abandoned
+            // and the rest of its output is NaN (as in sample_kernel)
+            report_error(a.err, stream, ctx.err, ctx.err_vals);
+            ctx.err = 0;
+            for (; d < n; ++d) row[d] = out_nan<OutT>();
+            store_state(a.state, stream, rng.s);
+            have = false;
+          } else if (st == 1) {
+            row[d++] = static_cast<OutT>(value);
+            if (d == n) { store_state(a.state, stream, rng.s); have = false; }
+          } else if (st == 2) {
+            parked = true;
+          }
+        }
+        m_park = __ballot_sync(0xffffffffu, parked);
+        const unsigned m_next = __ballot_sync(0xffffffffu, have && !parked);
+        if (m_park != 0 && (__popc(m_park) >= 16 || m_next == 0)) {
+          if (parked) {
+            T value;
+            if (D::slow(prep, ctx, cand, value)) {
+              row[d++] = static_cast<OutT>(value);
+              if (d == n) { store_state(a.state, stream, rng.s); have = false; }
+            }
+            parked = false;
+          }
+        }
+      }
+    } else {
     const unsigned n_chunks = (count + 31) / 32;
 #pragma unroll 1
     for (;;) {
@@ -215,21 +314,30 @@ sorted_sample_kernel(const SampleArgs a) {
       }
       if (touched) store_state(a.state, stream, rng.s);
     }
+    }
     __syncthreads();                                 // par_s / s_order are reused by the next tile
   }
 }
 
-template <class D, typename T, typename OutT>
-cudaError_t launch_sorted_t(const SampleArgs& a, int sm_count, cudaStream_t st) {
+template <class D, typename T, typename OutT, bool PERSIST>
+cudaError_t launch_sorted_v(const SampleArgs& a, int sm_count, cudaStream_t st) {
   const size_t smem = sorted_smem_bytes(D::NP, D::TABLES);
-  cudaError_t e = cudaFuncSetAttribute(sorted_sample_kernel<D, T, OutT>,
+  cudaError_t e = cudaFuncSetAttribute(sorted_sample_kernel<D, T, OutT, PERSIST>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   const unsigned long long tiles = (a.n_streams + kSortTile - 1) / kSortTile;
   const unsigned long long cap = static_cast<unsigned long long>(sm_count) * 8;
   const unsigned grid = static_cast<unsigned>(tiles < cap ? (tiles ? tiles : 1) : cap);
-  sorted_sample_kernel<D, T, OutT><<<grid, kSortBlock, smem, st>>>(a);
+  sorted_sample_kernel<D, T, OutT, PERSIST><<<grid, kSortBlock, smem, st>>>(a);
   return cudaGetLastError();
+}
+template <class D, typename T, typename OutT>
+cudaError_t launch_sorted_t(const SampleArgs& a, int sm_count, cudaStream_t st) {
+  if constexpr (D::DEFER) {
+    // persistent lanes up to D::SORT_PERSIST_MAX_N draws per stream (samplers.cuh)
+    if (a.n_samples <= static_cast<unsigned long long>(D::SORT_PERSIST_MAX_N)) return launch_sorted_v<D, T, OutT, true>(a, sm_count, st);
+  }
+  return launch_sorted_v<D, T, OutT, false>(a, sm_count, st);
 }
 
 // Is the sorted kernel the right one for this launch?  Only when the

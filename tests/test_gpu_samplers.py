@@ -317,6 +317,27 @@ def test_error_text_and_partial_advance(mb, name, pars, message, offender):
         assert np.array_equal(after, ost)
 
 
+@pytest.mark.parametrize("ns", [1, 16])
+def test_errors_in_the_regime_sorted_kernels(mb, oracle, ns):
+    """An invalid parameter in the middle of 5000 per-stream parameter sets (the regime-sorting
+    kernel, its persistent-lane variant at one draw per stream): the reference's message,
+    streams before the offender advanced exactly like the reference, the offender and later
+    streams untouched (ref: src/random.cpp:211-228)."""
+    n, bad = 5000, 3333
+    pars = [p.copy() for p in sampler_cases(n)["binomial"]]
+    pars[1][bad] = 1.5
+    rng = mb.monty_rng_create(n, 7)
+    before = states_of(mb, rng)
+    with pytest.raises(mb.MontyError, match=r"Invalid call to binomial with n = .*, p = 1\.5"):
+        mb.random._sample(rng, "binomial", ns, pars)
+    after = states_of(mb, rng)
+    ost = oracle.seed_states(7, n)
+    good = [p[:bad] for p in pars]
+    oracle.sample("binomial", ost[:bad], ns, good)          # a view: advanced in place
+    assert np.array_equal(after[:bad], ost[:bad])
+    assert np.array_equal(after[bad:], before[bad:])
+
+
 def test_parameter_length_errors(mb):
     """ref: tests/testthat/test-random.R:105-120, src/random.cpp:21-42."""
     rng = mb.monty_rng_create(5, 1)
