@@ -385,6 +385,170 @@ density_tile_kernel(const DensityArgs a, const unsigned long long n_full_tiles) 
   }
 }
 
+// ---------------------------------------------------------------------------
+// The sorted kernel: the densities whose cost is lgamma of NON-INTEGER arguments
+// (negative binomial, beta-binomial).  glibc's lgamma is a different program below 8
+// (rational pieces) and above (Stirling); lgamma_positive_batch evaluates the Stirling
+// range for every argument of an observation and then works the smaller arguments off
+// one per lane per trip, so a warp makes as many trips as its WORST observation has
+// small arguments while most lanes idle (ncu: 21 of 32 lanes active, nbinom; a warp of
+// 32 random observations almost always contains one with 2+ small arguments).
+// Here a CTA classifies a tile of 2048 observations by their number of small arguments
+// (a few adds and compares), partitions the tile by that count -- a STABLE partition from
+// warp votes and one prefix sum, so the order and with it the fused sum stay reproducible --
+// and its warps evaluate 32-observation chunks of the sorted order: a chunk is (nearly)
+// pure in its class and makes exactly that many trips.  Per observation nothing changes:
+// the same density_compute() on the same values.
+// ---------------------------------------------------------------------------
+constexpr int kDsTile = 2048;
+constexpr int kDsPer = kDsTile / kDensBlock;      // observations per thread in the classification
+constexpr int kDsClasses = 17;                     // 4 x 4 (arguments in [2, 8), arguments below 2 -- the two loops of
+                                                   // lgamma_positive_batch), 16 = beyond the end of the array
+
+template <int DENS> struct DensSorted {
+  static constexpr bool value = DENS == MB200_DENS_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_NEGATIVE_BINOMIAL_PROB ||
+                                DENS == MB200_DENS_BETA_BINOMIAL_AB || DENS == MB200_DENS_BETA_BINOMIAL_PROB;
+};
+
+// class of an observation: min(3, arguments in [2, 8)) * 4 + min(3, arguments below 2) --
+// the trip counts of the two loops of lgamma_positive_batch (the class only steers which
+// observations share a warp: it never changes a value, so it may be approximate)
+__device__ __forceinline__ void dens_count_arg(double v, int& mid, int& low) {
+  mid += (v >= 2.0 && v < 8.0);
+  low += (v < 2.0);
+}
+template <int DENS>
+__device__ __forceinline__ int dens_small_args(double x, const double* p) {
+  int mid = 0, low = 0;
+  if constexpr (DENS == MB200_DENS_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_NEGATIVE_BINOMIAL_PROB) {
+    dens_count_arg(p[0], mid, low);
+    dens_count_arg(x + p[0], mid, low);
+  } else {
+    double a = p[1], b = p[2];
+    if constexpr (DENS == MB200_DENS_BETA_BINOMIAL_PROB) {
+      const double k = 1.0 / p[2] - 1.0;
+      a = p[1] * k;
+      b = (1.0 - p[1]) * k;
+    }
+    const double pp = x + a, qq = p[0] - x + b;
+    dens_count_arg(pp, mid, low);
+    dens_count_arg(qq, mid, low);
+    dens_count_arg(pp + qq, mid, low);
+    dens_count_arg(a, mid, low);
+    dens_count_arg(b, mid, low);
+    dens_count_arg(a + b, mid, low);
+  }
+  return (mid < 3 ? mid : 3) * 4 + (low < 3 ? low : 3);
+}
+
+template <int DENS>
+__global__ void __launch_bounds__(kDensBlock)
+density_sorted_kernel(const DensityArgs a) {
+  using Cn = DensCanon<DENS>;
+  constexpr int NPD = DensNP<DENS>::value;
+  extern __shared__ __align__(16) unsigned char ds_smem[];
+  __shared__ unsigned short s_order[kDsTile];
+  __shared__ unsigned short s_cnt[kDsClasses * kDsPer * (kDensBlock / 32)];      // [class][round][warp]
+  // the tile's inputs in their own types: array j at ds_off(j)
+  auto ds_off = [](int j) { unsigned o = 0; for (int i = 0; i < j; ++i) o += kDsTile * (Cn::is_int(i) ? 4u : 8u); return o; };
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool lg = a.log != 0;
+  const void* src[1 + NPD];
+  src[0] = a.x;
+#pragma unroll
+  for (int k = 0; k < NPD; ++k) src[k + 1] = a.par[k];
+  auto lds_arg = [&](int j, unsigned e) -> double {
+    return Cn::is_int(j) ? static_cast<double>(reinterpret_cast<const int*>(ds_smem + ds_off(j))[e])
+                         : reinterpret_cast<const double*>(ds_smem + ds_off(j))[e];
+  };
+
+  double acc = 0.0;
+  const unsigned long long n_tiles = (a.n + kDsTile - 1) / kDsTile;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long base = tile * kDsTile;
+    const unsigned count = (a.n - base) < kDsTile ? static_cast<unsigned>(a.n - base) : kDsTile;
+    for (int i = tid; i < kDsClasses * kDsPer * (kDensBlock / 32); i += kDensBlock) s_cnt[i] = 0;
+    __syncthreads();
+    // 1. inputs -> shared memory (coalesced), class and rank inside (class, round, warp)
+    unsigned cls[kDsPer], rank[kDsPer];
+#pragma unroll
+    for (int i = 0; i < kDsPer; ++i) {
+      const unsigned e = static_cast<unsigned>(i * kDensBlock + tid);
+      cls[i] = kDsClasses - 1;
+      if (e < count) {
+        double xv, pv[NPD];
+#pragma unroll
+        for (int j = 0; j <= NPD; ++j) {
+          double v;
+          if (Cn::is_int(j)) {
+            const int iv = static_cast<const int*>(src[j])[base + e];
+            reinterpret_cast<int*>(ds_smem + ds_off(j))[e] = iv;
+            v = static_cast<double>(iv);
+          } else {
+            v = static_cast<const double*>(src[j])[base + e];
+            reinterpret_cast<double*>(ds_smem + ds_off(j))[e] = v;
+          }
+          if (j == 0) xv = v; else pv[j - 1] = v;
+        }
+        const int c = dens_small_args<DENS>(xv, pv);
+        cls[i] = static_cast<unsigned>(c < 0 ? 0 : (c > kDsClasses - 2 ? kDsClasses - 2 : c));
+      }
+      const unsigned same = __match_any_sync(0xffffffffu, cls[i]);
+      rank[i] = static_cast<unsigned>(__popc(same & ((1u << lane) - 1u)));
+      if (rank[i] == 0) s_cnt[(cls[i] * kDsPer + i) * (kDensBlock / 32) + warp] = static_cast<unsigned short>(__popc(same));
+    }
+    __syncthreads();
+    // 2. exclusive prefix sum over (class, round, warp): 512 counts, one warp, 16 per lane
+    if (warp == 0) {
+      constexpr int kEach = kDsClasses * kDsPer * (kDensBlock / 32) / 32;
+      unsigned local[kEach], sum = 0;
+#pragma unroll
+      for (int q = 0; q < kEach; ++q) { local[q] = s_cnt[lane * kEach + q]; sum += local[q]; }
+      unsigned incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+      }
+      unsigned run = incl - sum;
+#pragma unroll
+      for (int q = 0; q < kEach; ++q) { s_cnt[lane * kEach + q] = static_cast<unsigned short>(run); run += local[q]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kDsPer; ++i) {
+      const unsigned pos = s_cnt[(cls[i] * kDsPer + i) * (kDensBlock / 32) + warp] + rank[i];
+      if (pos < kDsTile) s_order[pos] = static_cast<unsigned short>(i * kDensBlock + tid);
+    }
+    __syncthreads();
+    // 3. warps evaluate 32-observation chunks of the sorted order (chunk c -> warp c % 8)
+    for (unsigned k = static_cast<unsigned>(tid); k < count; k += kDensBlock) {
+      const unsigned e = s_order[k];
+      const double xv = lds_arg(0, e);
+      double pv[NPD];
+#pragma unroll
+      for (int j = 0; j < NPD; ++j) pv[j] = lds_arg(j + 1, e);
+      const double v = density_compute<DENS, double>(xv, pv, lg);
+      if (a.out) a.out[base + e] = v;
+      acc += v;
+    }
+    __syncthreads();                      // the tile buffers are reused
+  }
+  if (a.partial) {
+    __shared__ double warp_sum[kDensBlock / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) warp_sum[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < kDensBlock / 32; ++w) sum += warp_sum[w];
+      a.partial[blockIdx.x] = sum;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ sum) {
   __shared__ double sh[256];
@@ -448,6 +612,27 @@ static cudaError_t launch_density_t(int real_type, const DensityArgs& a, int sm_
   if (!generic_only && tiled_applies<DENS>(a)) {
     return real_type == MB200_REAL_F32 ? launch_tiled<DENS, float>(a, sm_count, grid_out, st)
                                        : launch_tiled<DENS, double>(a, sm_count, grid_out, st);
+  }
+  if constexpr (DensSorted<DENS>::value) {
+    // double, the reference's own argument types, enough observations to be worth sorting
+    using Cn = DensCanon<DENS>;
+    bool canon = real_type != MB200_REAL_F32 && a.n >= 4ull * kDsTile && (a.x_is_i32 != 0) == Cn::is_int(0);
+    for (int k = 0; k < DensNP<DENS>::value; ++k) canon = canon && (a.par_is_i32[k] != 0) == Cn::is_int(k + 1);
+    if (!generic_only && canon) {
+      size_t smem = 0;
+      for (int j = 0; j <= DensNP<DENS>::value; ++j) smem += kDsTile * (Cn::is_int(j) ? 4u : 8u);
+      const unsigned long long tiles = (a.n + kDsTile - 1) / kDsTile;
+      int per_sm = static_cast<int>((200u * 1024u) / (smem + 6 * 1024));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 5 ? 5 : per_sm);
+      unsigned long long grid = static_cast<unsigned long long>(sm_count) * per_sm;
+      if (grid > tiles) grid = tiles;
+      cudaError_t e = cudaFuncSetAttribute(density_sorted_kernel<DENS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+      density_sorted_kernel<DENS><<<static_cast<unsigned>(grid), kDensBlock, smem, st>>>(a);
+      *grid_out = static_cast<int>(grid);
+      return cudaGetLastError();
+    }
   }
   const int grid = density_grid(a.n, sm_count);
   *grid_out = grid;
