@@ -10,7 +10,7 @@ NTOP=60 sh tools/ncu_one.sh hypergeometric_d16 --dist hypergeometric --streams 2
 NTOP=60 sh tools/ncu_one.sh binomial_d1 --dist binomial --streams 4194304 --draws 1
 NTOP=60 sh tools/ncu_one.sh gamma_d16 --dist gamma_scale --streams 2097152 --draws 16
 NTOP=60 sh tools/ncu_cmd.sh density_poisson density_tile 1 python tools/density_run.py poisson 250000000 2
-NTOP=60 sh tools/ncu_cmd.sh density_nbinom density_kernel 1 python tools/density_run.py negative_binomial_mu 100000000 2
+NTOP=60 sh tools/ncu_cmd.sh density_nbinom "density_sorted|density_kernel" 1 python tools/density_run.py negative_binomial_mu 100000000 2
 sh tools/ncu_counts.sh
 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/launch_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv \
