@@ -400,7 +400,12 @@ density_tile_kernel(const DensityArgs a, const unsigned long long n_full_tiles) 
 // pure in its class and makes exactly that many trips.  Per observation nothing changes:
 // the same density_compute() on the same values.
 // ---------------------------------------------------------------------------
-constexpr int kDsTile = 2048;
+// observations per tile (measured, nbinom / beta-binomial Gobs/s: 1024: 44.7 / 12.8, 2048: 45.2 / 13.5,
+// 4096: 33.5 / 7.9 -- two CTAs per SM; handing the chunks out dynamically with per-chunk sums: 41.1 / 13.2)
+#ifndef MB200_DS_TILE
+#define MB200_DS_TILE 2048
+#endif
+constexpr int kDsTile = MB200_DS_TILE;
 constexpr int kDsPer = kDsTile / kDensBlock;      // observations per thread in the classification
 constexpr int kDsClasses = 17;                     // 4 x 4 (arguments in [2, 8), arguments below 2 -- the two loops of
                                                    // lgamma_positive_batch), 16 = beyond the end of the array
