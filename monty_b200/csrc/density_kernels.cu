@@ -412,7 +412,9 @@ constexpr int kDsClasses = 17;                     // 4 x 4 (arguments in [2, 8)
 
 template <int DENS> struct DensSorted {
   static constexpr bool value = DENS == MB200_DENS_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_NEGATIVE_BINOMIAL_PROB ||
-                                DENS == MB200_DENS_BETA_BINOMIAL_AB || DENS == MB200_DENS_BETA_BINOMIAL_PROB;
+                                DENS == MB200_DENS_BETA_BINOMIAL_AB || DENS == MB200_DENS_BETA_BINOMIAL_PROB ||
+                                DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_PROB ||
+                                DENS == MB200_DENS_GAMMA_RATE || DENS == MB200_DENS_GAMMA_SCALE || DENS == MB200_DENS_BETA;
 };
 
 // class of an observation: min(3, arguments in [2, 8)) * 4 + min(3, arguments below 2) --
@@ -428,6 +430,15 @@ __device__ __forceinline__ int dens_small_args(double x, const double* p) {
   if constexpr (DENS == MB200_DENS_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_NEGATIVE_BINOMIAL_PROB) {
     dens_count_arg(p[0], mid, low);
     dens_count_arg(x + p[0], mid, low);
+  } else if constexpr (DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_MU || DENS == MB200_DENS_ZI_NEGATIVE_BINOMIAL_PROB) {
+    dens_count_arg(p[1], mid, low);              // (pi0, size, mu | prob)
+    dens_count_arg(x + p[1], mid, low);
+  } else if constexpr (DENS == MB200_DENS_GAMMA_RATE || DENS == MB200_DENS_GAMMA_SCALE) {
+    dens_count_arg(p[0], mid, low);              // lgamma(shape)
+  } else if constexpr (DENS == MB200_DENS_BETA) {
+    dens_count_arg(p[0], mid, low);              // lbeta(a, b)
+    dens_count_arg(p[1], mid, low);
+    dens_count_arg(p[0] + p[1], mid, low);
   } else {
     double a = p[1], b = p[2];
     if constexpr (DENS == MB200_DENS_BETA_BINOMIAL_PROB) {

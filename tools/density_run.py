@@ -11,7 +11,17 @@ name = sys.argv[1] if len(sys.argv) > 1 else "poisson"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 250_000_000
 rep = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda", 0)
-x, pars = density_inputs_torch(name, n, 0, dev)
+if name in ("poisson", "negative_binomial_mu", "beta_binomial_prob"):
+    x, pars = density_inputs_torch(name, n, 0, dev)
+else:                                   # other densities: simple uniform inputs (development aid)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    u = lambda lo, hi: lo + (hi - lo) * torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    xi = lambda hi: torch.randint(0, hi, (n,), dtype=torch.int32, device=dev, generator=g)
+    x, pars = {"gamma_rate": lambda: (u(0.05, 20), [u(0.3, 30), u(0.5, 2)]),
+               "gamma_scale": lambda: (u(0.05, 20), [u(0.3, 30), u(0.5, 2)]),
+               "beta": lambda: (u(0.01, 0.99), [u(0.2, 20), u(0.2, 20)]),
+               "zi_negative_binomial_mu": lambda: (xi(60), [u(0, 1), u(0.5, 50), u(0.1, 100)]),
+               "negative_binomial_prob": lambda: (xi(60), [u(0.5, 50), u(0.05, 0.95)])}[name]()
 for _ in range(rep):
     t = density_sum_dev(name, x, pars)
 torch.cuda.synchronize()
